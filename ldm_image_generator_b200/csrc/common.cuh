@@ -1,0 +1,78 @@
+// Shared definitions for the libldmb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+// ---- A-operand addressing
+enum { AM_ROWS = 0,    // A is a row-major [M, K] matrix (1x1 convolution on NHWC activations)
+       AM_CONV3 = 1 }; // A is an NHWC tensor; K = 9*cC, k = tap*cC + c, 3x3 window, zero padding 1
+// ---- epilogues
+enum { EPI_STORE = 0,      // out(T)[m,n]   = act(acc + bias) (+ res)
+       EPI_STORE_F32 = 1,  // out(f32)[m,n] = act(acc + bias)
+       EPI_ACCUM_F32 = 2,  // out(f32)[m,n] += acc + bias           (residual stream)
+       EPI_REGLU = 3,      // out(T)[m,j]   = (acc_a + bias_a) * relu(acc_b + bias_b)   (modules.py:15)
+       EPI_CONVT = 4 };    // ConvTranspose2d(k=2,s=2): column n = (dy*2+dx)*Cout + co scattered to pixel (2h+dy, 2w+dx)
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+// One GEMM-shaped launch: acc[M, N] = A[M, K] * W[N, K]^T, then an epilogue.  Used by both the
+// CUDA-core (validation) kernel and the tcgen05 kernel so that they are interchangeable.
+struct GemmDesc {
+  const void* A; long long lda;        // AM_ROWS: row stride (elements). AM_CONV3: channels per pixel of the NHWC tensor
+  int amode; int cH, cW, cC;           // AM_CONV3: image height/width and channels per (group of the) convolution
+  const void* W; long long ldw;        // weights [rows, K], row stride in elements
+  const float* bias;                   // indexed like the weight rows
+  void* out; long long ldo;
+  const void* res; long long ldr;      // optional residual in T, added after the activation (EPI_STORE)
+  int M, N, K;                         // N counts accumulator columns
+  int epi, act; float slope;
+  // expert selection (RandomMoE, modules.py:34-36): which rows of the stacked expert weights a slot uses
+  int sel;                             // 0 none; 1 slot = n / sel_span (a|b GEMM); 2 slot = k / sel_span (c GEMM)
+  int sel_span;
+  int sel_rows[3];                     // first weight row (and bias index) of slot 0..2
+  int glu_chunk;                       // EPI_REGLU: a and b columns interleaved in chunks of this many columns
+  // grid.z batching (grouped convolution groups, per-block FiLM projections)
+  int batch; long long a_koff_b, w_row_b, out_off_b, bias_off_b;
+  int ctH, ctW, ctC;                   // EPI_CONVT: input height, width, output channels
+};
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_LEAKY) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// Weight row / bias index of accumulator column n (for sel != 2).
+__device__ __forceinline__ int wrow_of_col(const GemmDesc& d, int z, int n) {
+  int row = n;
+  if (d.sel == 1) row = d.sel_rows[n / d.sel_span] + n % d.sel_span;
+  return row + (int)(z * d.w_row_b);
+}
+// Bias of accumulator column n (sums the per-slot biases for sel == 2).
+__device__ __forceinline__ float bias_of_col(const GemmDesc& d, int z, int n) {
+  if (d.bias == nullptr) return 0.f;
+  const float* b = d.bias + z * d.bias_off_b;
+  if (d.sel == 2) {
+    float s = 0.f;
+    for (int q = 0; q < d.K / d.sel_span; ++q) s += b[d.sel_rows[q] + n];
+    return s;
+  }
+  if (d.sel == 1) return b[d.sel_rows[n / d.sel_span] + n % d.sel_span];
+  return b[n];
+}
+// EPI_CONVT destination offset (elements) of (input pixel m, accumulator column n).
+__device__ __forceinline__ long long convt_offset(const GemmDesc& d, int m, int n) {
+  const int HW = d.ctH * d.ctW;
+  const int b = m / HW, r = m % HW, h = r / d.ctW, w = r % d.ctW;
+  const int q = n / d.ctC, co = n % d.ctC, dy = q >> 1, dx = q & 1;
+  return (((long long)b * (2 * d.ctH) + 2 * h + dy) * (2 * d.ctW) + 2 * w + dx) * d.ctC + co;
+}

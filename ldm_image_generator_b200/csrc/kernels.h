@@ -1,0 +1,59 @@
+// Host-side launchers of the libldmb200 kernels.  `is_bf16` selects the activation/weight type T
+// (bf16 in LDMB_BF16, float in LDMB_FP32_VALIDATE); the residual stream is always fp32.
+#pragma once
+#include "common.cuh"
+
+struct TcContext;   // tcgen05 GEMM state (tensor-map encoder entry point, SM count, fault flag)
+
+// ---- GEMM-shaped work
+cudaError_t launch_gemm_simt(const GemmDesc& d, bool is_bf16, cudaStream_t s);
+// Returns cudaErrorNotSupported when the shape cannot be tiled for tcgen05 (caller falls back to
+// the CUDA-core kernel, which only happens for toy channel counts).
+TcContext* tc_context_create(int device, char* err, int errlen);
+void tc_context_destroy(TcContext*);
+cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s);
+bool tc_supported(const GemmDesc& d);
+int tc_read_fault(TcContext* ctx, cudaStream_t s);
+
+// ---- weight repack: dst[T] (4-d, dst strides) = src[fp32] (4-d, src strides)
+cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int dims[4],
+                          const long long sstr[4], const long long dstr[4], cudaStream_t s);
+
+// ---- UNet pieces
+// encoder_first (unet.py:77,90): x NCHW fp32 [B,Cin,H*s,W*s] -> out fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]
+cudaError_t launch_stem(const float* x, const float* w, const float* bias, float* out,
+                        int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
+// ChannelNorm + FiLM (modules.py:23-25, unet.py:22): out(T)[m,c] = norm(x[m,:])[c]*film[row,c] + film[row,C+c]
+// film row = t_index[m / HW] * HW + m % HW  (t_index may be NULL -> 0)
+cudaError_t launch_norm_film(const float* x, const float* film, const int* t_index, void* out, bool is_bf16,
+                             int M, int C, int HW, float eps, cudaStream_t st);
+// emb(T)[ti*HW + p][0:C] = pe[p][:],  [C:2C] = te[ti][:]      (unet.py:19)
+cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool is_bf16, int n_t, int HW, int C,
+                             cudaStream_t st);
+// AvgPool2d(2) on NHWC fp32 -> T (feeds the encoder ch_conv GEMM; pool and 1x1 conv commute, unet.py:83)
+cudaError_t launch_pool_cast(const float* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cudaStream_t st);
+// x[b,h,w,:] += ylow[b,h/2,w/2,:]   (nearest Upsample(2) commuted behind the 1x1 conv + skip add, unet.py:85,100-101)
+cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st);
+// Window attention core (attention.py:13-85 + torch MHA): qkv(T) [M,3C] (+ in_proj bias for pad tokens),
+// key bias from xm(T) channel 0 when shift != 0, writes att(T) [M,C]
+cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, bool is_bf16,
+                                    int B, int H, int W, int C, int head_dim, int win_h, int win_w, int shift,
+                                    cudaStream_t st);
+// decoder_last ConvTranspose (unet.py:78,102) fused with the DDIM update (ddpm.py:81-91).
+// x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; xin/out/noise NCHW fp32 [B,Cin,H*s,W*s]; mode 0 = eps only.
+struct DdimScalars { float c_eps_in, c_div, c_x0, c_eps_out, sigma; int final_step; int enabled; };
+cudaError_t launch_final(const float* x, const float* w, const float* bias, const float* xin, const float* noise,
+                         float* out, DdimScalars co, int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
+
+// ---- VAE pieces
+// 1x1 conv from an NCHW fp32 tensor with few channels (latent 8 / RGB 3) into NHWC T
+cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float* bias, void* out, bool is_bf16,
+                                     int B, int Cin, int H, int W, int Cout, cudaStream_t st);
+// 1x1 conv from NHWC T down to few channels, NCHW fp32 out; optionally + bilinear_up2(prev) (vae.py:131) and
+// the uint8 HWC image of sample_ldm.py:75-77
+cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* w, const float* bias,
+                                      const float* prev, float* out, uint8_t* out_u8,
+                                      int B, int H, int W, int C, int Cout, cudaStream_t st);
+// AvgPool2d(2) NHWC T -> T (vae.py:88)
+cudaError_t launch_pool_t(const void* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st);

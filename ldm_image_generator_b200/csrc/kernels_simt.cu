@@ -1,0 +1,609 @@
+// CUDA-core kernels of libldmb200: the fp32 validation GEMM/convolution, and every
+// HBM-bound (norm / elementwise / gather) kernel of the sampling path.
+// Reference lines cited are under /root/reference.
+#include "kernels.h"
+
+#include <math.h>
+
+namespace {
+
+// =====================================================================================
+// Generic GEMM / implicit-GEMM convolution on CUDA cores (64x64x16 tiles, 4x4 per thread).
+// The LDMB_FP32_VALIDATE implementation of every contraction, and the bf16 fallback for
+// toy channel counts that cannot be tiled for tcgen05.
+// =====================================================================================
+template <typename T, int AMODE, bool GLU>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmDesc d) {
+  constexpr int BM = 64, BN = 64, BK = 16, NW = GLU ? 2 : 1;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[NW][BK][BN + 4];
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int NL = GLU ? d.N / 2 : d.N;          // logical output columns
+  const int G = d.glu_chunk;
+  const T* __restrict__ A = reinterpret_cast<const T*>(d.A);
+  const T* __restrict__ W = reinterpret_cast<const T*>(d.W);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[NW][4][4];
+#pragma unroll
+  for (int w = 0; w < NW; ++w)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[w][i][j] = 0.f;
+
+  for (int k0 = 0; k0 < d.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256, r = idx >> 4, kk = idx & 15;
+      const int m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (m < d.M && k < d.K) {
+        if (AMODE == AM_ROWS) {
+          v = to_f(A[(long long)m * d.lda + z * d.a_koff_b + k]);
+        } else {
+          const int tap = k / d.cC, c = k % d.cC;
+          const int hw = d.cH * d.cW, b = m / hw, rem = m % hw;
+          const int hh = rem / d.cW + tap / 3 - 1, ww = rem % d.cW + tap % 3 - 1;
+          if (hh >= 0 && hh < d.cH && ww >= 0 && ww < d.cW)
+            v = to_f(A[(((long long)b * d.cH + hh) * d.cW + ww) * d.lda + z * d.a_koff_b + c]);
+        }
+      }
+      As[kk][r] = v;
+    }
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * 256, c = idx >> 4, kk = idx & 15;
+        const int j = j0 + c, k = k0 + kk;
+        float v = 0.f;
+        if (j < NL && k < d.K) {
+          const int n = GLU ? (j / G) * 2 * G + j % G + w * G : j;
+          long long row; int col = k;
+          if (d.sel == 2) { row = d.sel_rows[k / d.sel_span] + n + z * d.w_row_b; col = k % d.sel_span; }
+          else row = wrow_of_col(d, z, n);
+          v = to_f(W[row * d.ldw + col]);
+        }
+        Ws[w][kk][c] = v;
+      }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[NW][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[w][j] = Ws[w][kk][tx * 4 + j];
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[w][i][j] = fmaf(a[i], b[w][j], acc[w][i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= d.M) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + tx * 4 + jj;
+      if (j >= NL) continue;
+      if (GLU) {
+        const int na = (j / G) * 2 * G + j % G, nb = na + G;
+        const float va = acc[0][i][jj] + bias_of_col(d, z, na);
+        const float vb = acc[NW - 1][i][jj] + bias_of_col(d, z, nb);
+        reinterpret_cast<T*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = from_f<T>(va * fmaxf(vb, 0.f));
+      } else {
+        float v = acc[0][i][jj] + bias_of_col(d, z, j);
+        if (d.epi == EPI_ACCUM_F32) {
+          float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + j;
+          *o += v;
+        } else if (d.epi == EPI_STORE_F32) {
+          reinterpret_cast<float*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = apply_act(v, d.act, d.slope);
+        } else if (d.epi == EPI_CONVT) {
+          reinterpret_cast<T*>(d.out)[convt_offset(d, m, j)] = from_f<T>(apply_act(v, d.act, d.slope));
+        } else {
+          v = apply_act(v, d.act, d.slope);
+          if (d.res) v += to_f(reinterpret_cast<const T*>(d.res)[(long long)m * d.ldr + j]);
+          reinterpret_cast<T*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = from_f<T>(v);
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+cudaError_t gemm_simt_dispatch(const GemmDesc& d, cudaStream_t s) {
+  const bool glu = d.epi == EPI_REGLU;
+  const int NL = glu ? d.N / 2 : d.N;
+  dim3 grid((NL + 63) / 64, (d.M + 63) / 64, d.batch > 0 ? d.batch : 1);
+  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
+  if (d.amode == AM_ROWS) {
+    if (glu) gemm_simt_kernel<T, AM_ROWS, true><<<grid, 256, 0, s>>>(d);
+    else gemm_simt_kernel<T, AM_ROWS, false><<<grid, 256, 0, s>>>(d);
+  } else {
+    if (glu) return cudaErrorNotSupported;
+    gemm_simt_kernel<T, AM_CONV3, false><<<grid, 256, 0, s>>>(d);
+  }
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// weight repack
+// =====================================================================================
+struct Repack4 { int dims[4]; long long ss[4]; long long ds[4]; };
+template <typename T>
+__global__ void repack_kernel(const float* __restrict__ src, T* __restrict__ dst, Repack4 r, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int i3 = t % r.dims[3]; t /= r.dims[3];
+    const int i2 = t % r.dims[2]; t /= r.dims[2];
+    const int i1 = t % r.dims[1]; t /= r.dims[1];
+    const int i0 = (int)t;
+    dst[i0 * r.ds[0] + i1 * r.ds[1] + i2 * r.ds[2] + i3 * r.ds[3]] =
+        from_f<T>(src[i0 * r.ss[0] + i1 * r.ss[1] + i2 * r.ss[2] + i3 * r.ss[3]]);
+  }
+}
+
+// =====================================================================================
+// ChannelNorm + FiLM: one warp per pixel, the row lives in registers (C <= 2048), 16-byte loads.
+// Algorithmic bytes per pixel: 4C read (fp32 residual) + sizeof(T)*C written (+ the L2-resident FiLM row).
+// =====================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> struct Pack4;
+template <> struct Pack4<float> {
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
+};
+template <> struct Pack4<bf16> {
+  static __device__ __forceinline__ void store(bf16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict__ x, const float* __restrict__ film,
+                                                        const int* __restrict__ t_index, T* __restrict__ out,
+                                                        int M, int C, int HW, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps_per_grid) {
+    const float* xr = x + (long long)m * C;
+    float4 v[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (c < C) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (c < C) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float sd = sqrtf(warp_sum(sq) / (float)(C - 1) + eps);   // unbiased variance (modules.py:24)
+    const int trow = (t_index ? t_index[m / HW] : 0) * HW + m % HW;
+    const float* fr = film + (long long)trow * 2 * C;
+    T* orow = out + (long long)m * C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = i * 128 + lane * 4;
+      if (c < C) {
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(fr + c));
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(fr + C + c));
+        Pack4<T>::store(orow + c, (v[i].x / sd) * mu.x + bi.x, (v[i].y / sd) * mu.y + bi.y,
+                        (v[i].z / sd) * mu.z + bi.z, (v[i].w / sd) * mu.w + bi.w);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void emb_build_kernel(const float* __restrict__ pe, const float* __restrict__ te, T* __restrict__ emb,
+                                 int n_t, int HW, int C) {
+  const long long total = (long long)n_t * HW * 2 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (2 * C));
+    const long long row = i / (2 * C);
+    const int p = (int)(row % HW), ti = (int)(row / HW);
+    emb[i] = from_f<T>(c < C ? pe[(long long)p * C + c] : te[(long long)ti * C + (c - C)]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void pool2_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const TI* p = x + (((long long)b * H + 2 * ho) * W + 2 * wo) * C + c;
+    const float s = (to_f(p[0]) + to_f(p[C])) + (to_f(p[(long long)W * C]) + to_f(p[(long long)W * C + C]));
+    out[i] = from_f<TO>(s * 0.25f);
+  }
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(x[i]);
+}
+
+__global__ void upsample_add_kernel(float* __restrict__ x, const float* __restrict__ ylow, int B, int H, int W, int C4) {
+  // C4 = C / 4 (float4 lanes)
+  const long long total = (long long)B * H * W * C4;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  const float4* y4 = reinterpret_cast<const float4*>(ylow);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    const float4 y = __ldg(y4 + (((long long)b * (H / 2) + h / 2) * (W / 2) + w / 2) * C4 + c);
+    float4 v = x4[i];
+    v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+    x4[i] = v;
+  }
+}
+
+// =====================================================================================
+// Window attention core.  One CTA per (image, window, head); thread i < L owns query i.
+// Index arithmetic replaces the reference's pad / roll / split / concat copies (attention.py:19-58):
+// slot (si,sj) of window (wi,wj) is rolled position r=(wi*wh+si, wj*ww+sj), i.e. padded position
+// p=((r_i-s) mod Hp, (r_j-s) mod Wp); pad positions (p_i>=H or p_j>=W) carry q/k/v = in_proj bias.
+// Key bias: shift==0 -> pad keys masked (-inf); shift!=0 -> + xm[channel 0] at ((p_i-s) mod Hp, (p_j-s) mod Wp)
+// (attention.py:40 rolls the activation into `mask`), 0 where that position is padding.
+// =====================================================================================
+template <typename T, int D>
+__global__ void __launch_bounds__(64) window_attention_kernel(const T* __restrict__ qkv, const T* __restrict__ xm,
+                                                             const float* __restrict__ b_in, T* __restrict__ att,
+                                                             int H, int W, int C, int wh, int ww, int shift,
+                                                             int Hp, int Wp) {
+  __shared__ float Ks[64][D + 1];
+  __shared__ float Vs[64][D + 1];
+  __shared__ float kb[64];
+  const int L = wh * ww;
+  const int nww = Wp / ww, nwin = (Hp / wh) * nww;
+  const int b = blockIdx.x / nwin, win = blockIdx.x % nwin;
+  const int wi = win / nww, wj = win % nww;
+  const int head = blockIdx.y;
+  const int tid = threadIdx.x;
+  long long m = -1;
+  bool active = tid < L;
+  if (active) {
+    const int si = tid / ww, sj = tid % ww;
+    const int pi = (wi * wh + si - shift + Hp) % Hp, pj = (wj * ww + sj - shift + Wp) % Wp;
+    const bool pad = pi >= H || pj >= W;
+    if (!pad) m = ((long long)b * H + pi) * W + pj;
+    const int off = head * D;
+    if (pad) {
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) { Ks[tid][dd] = b_in[C + off + dd]; Vs[tid][dd] = b_in[2 * C + off + dd]; }
+    } else {
+      const T* row = qkv + m * 3 * C;
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) { Ks[tid][dd] = to_f(row[C + off + dd]); Vs[tid][dd] = to_f(row[2 * C + off + dd]); }
+    }
+    float bias = 0.f;
+    if (shift == 0) {
+      bias = pad ? -INFINITY : 0.f;
+    } else {
+      const int qi = (pi - shift + Hp) % Hp, qj = (pj - shift + Wp) % Wp;
+      if (qi < H && qj < W) bias = to_f(xm[(((long long)b * H + qi) * W + qj) * C]);
+    }
+    kb[tid] = bias;
+  }
+  __syncthreads();
+  if (!active || m < 0) return;   // outputs at pad positions are cropped (attention.py:56)
+  float q[D], acc[D];
+  const float scale = (float)sqrt(1.0 / (double)D);
+  {
+    const T* row = qkv + m * 3 * C + head * D;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) { q[dd] = to_f(row[dd]) * scale; acc[dd] = 0.f; }
+  }
+  float mx = -INFINITY, den = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float bj = kb[j];
+    if (bj == -INFINITY) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) s = fmaf(q[dd], Ks[j][dd], s);
+    s += bj;
+    const float nm = fmaxf(mx, s);
+    const float corr = expf(mx - nm), p = expf(s - nm);
+    den = den * corr + p;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) acc[dd] = acc[dd] * corr + p * Vs[j][dd];
+    mx = nm;
+  }
+  T* o = att + m * C + head * D;
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) o[dd] = from_f<T>(acc[dd] * inv);
+}
+
+// =====================================================================================
+// Few-channel pointwise convolutions at the NCHW fp32 boundary
+// =====================================================================================
+// in: NCHW fp32 [B, Cin, H*s, W*s], k = stride = s (s = 1: 1x1 conv).  out: [B*H*W, Cout] in TO.
+template <typename TO>
+__global__ void pointwise_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, TO* __restrict__ out,
+                                    int B, int Cin, int H, int W, int s, int Cout) {
+  const long long total = (long long)B * H * W * Cout;
+  const int J = Cin * s * s;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long t = i / Cout;
+    const int ww = (int)(t % W); t /= W;
+    const int hh = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc = bias[co];
+    const float* wr = w + (long long)co * J;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int dy = 0; dy < s; ++dy)
+        for (int dx = 0; dx < s; ++dx)
+          acc = fmaf(x[(((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx],
+                     wr[(ci * s + dy) * s + dx], acc);
+    out[i] = from_f<TO>(acc);
+  }
+}
+
+// Reduce C channels of 32 consecutive NHWC pixels to J (<= 32) outputs each: warp w of 8 handles 4 pixels.
+// wmat is [C][J] (ConvTranspose layout) when w_cj, else [J][C] (Conv2d layout).  Result in smem e[J][32].
+template <typename T>
+__device__ __forceinline__ void reduce_pixels_32(const T* __restrict__ x, long long m0, long long M, int C, int J,
+                                                 const float* __restrict__ wmat, bool w_cj, float (*e)[33]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pp = 0; pp < 4; ++pp) {
+    const int p = warp * 4 + pp;
+    const long long m = m0 + p;
+    for (int j0 = 0; j0 < J; j0 += 8) {
+      float part[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[j] = 0.f;
+      if (m < M) {
+        for (int c = lane; c < C; c += 32) {
+          const float xv = to_f(x[m * C + c]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j0 + j < J) part[j] = fmaf(xv, w_cj ? wmat[(long long)c * J + j0 + j] : wmat[(long long)(j0 + j) * C + c], part[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = warp_sum(part[j]);
+        if (lane == 0 && j0 + j < J) e[j0 + j][p] = v;
+      }
+    }
+  }
+}
+
+// decoder_last (ConvTranspose2d k=s stride=s, unet.py:78,102) + DDIM update (ddpm.py:81-91)
+__global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, const float* __restrict__ xin,
+                                                    const float* __restrict__ noise, float* __restrict__ out,
+                                                    DdimScalars co, int B, int Cin, int H, int W, int s, int C0) {
+  __shared__ float e[32][33];
+  const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * 32;
+  const int J = Cin * s * s;
+  reduce_pixels_32<float>(x, m0, M, C0, J, w, true, e);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < J * 32; idx += blockDim.x) {
+    const int j = idx >> 5, p = idx & 31;
+    const long long m = m0 + p;
+    if (m >= M) continue;
+    const int ci = j / (s * s), dy = (j / s) % s, dx = j % s;
+    const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+    const long long o = (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
+    const float eps = e[j][p] + bias[ci];
+    float r = eps;
+    if (co.enabled) {
+      const float x0 = (xin[o] - co.c_eps_in * eps) / co.c_div;
+      if (co.final_step) r = x0;
+      else {
+        r = co.c_x0 * x0 + co.c_eps_out * eps;
+        r += co.sigma * (noise ? noise[o] : 0.f);
+      }
+    }
+    out[o] = r;
+  }
+}
+
+// NHWC T [B,H,W,C] -> NCHW fp32 [B,Cout,H,W] 1x1 conv (+ bilinear x2 of prev [B,Cout,H/2,W/2], + uint8 HWC copy)
+template <typename T>
+__global__ void __launch_bounds__(256) pointwise_out_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, const float* __restrict__ prev,
+                                                            float* __restrict__ out, uint8_t* __restrict__ out_u8,
+                                                            int B, int H, int W, int C, int Cout) {
+  __shared__ float e[32][33];
+  const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * 32;
+  reduce_pixels_32<T>(x, m0, M, C, Cout, w, false, e);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Cout * 32; idx += blockDim.x) {
+    const int j = idx >> 5, p = idx & 31;
+    const long long m = m0 + p;
+    if (m >= M) continue;
+    const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+    float v = e[j][p] + bias[j];
+    if (prev) {
+      // F.interpolate(scale_factor=2, 'bilinear', align_corners=False), vae.py:131
+      const int Hs = H / 2, Ws = W / 2;
+      const int i0 = hh >> 1, j0 = ww >> 1;
+      const int ia = (hh & 1) ? i0 : max(i0 - 1, 0), ib = (hh & 1) ? min(i0 + 1, Hs - 1) : i0;
+      const int ja = (ww & 1) ? j0 : max(j0 - 1, 0), jb = (ww & 1) ? min(j0 + 1, Ws - 1) : j0;
+      const float wa_h = (hh & 1) ? 0.75f : 0.25f, wa_w = (ww & 1) ? 0.75f : 0.25f;
+      const float* pp = prev + ((long long)b * Cout + j) * Hs * Ws;
+      const float top = wa_w * pp[ia * Ws + ja] + (1.f - wa_w) * pp[ia * Ws + jb];
+      const float bot = wa_w * pp[ib * Ws + ja] + (1.f - wa_w) * pp[ib * Ws + jb];
+      v += wa_h * top + (1.f - wa_h) * bot;
+    }
+    if (out) out[(((long long)b * Cout + j) * H + hh) * W + ww] = v;
+    if (out_u8) {
+      const float c = fminf(fmaxf(v, -1.f), 1.f);
+      out_u8[m * Cout + j] = (uint8_t)(c * 127.5f + 127.5f);   // truncation, sample_ldm.py:77
+    }
+  }
+}
+
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+cudaError_t launch_gemm_simt(const GemmDesc& d, bool is_bf16, cudaStream_t s) {
+  return is_bf16 ? gemm_simt_dispatch<bf16>(d, s) : gemm_simt_dispatch<float>(d, s);
+}
+
+cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int dims[4], const long long sstr[4],
+                          const long long dstr[4], cudaStream_t s) {
+  Repack4 r;
+  long long total = 1;
+  for (int i = 0; i < 4; ++i) { r.dims[i] = dims[i]; r.ss[i] = sstr[i]; r.ds[i] = dstr[i]; total *= dims[i]; }
+  if (total == 0) return cudaSuccess;
+  if (dst_bf16) repack_kernel<bf16><<<grid_for(total, 256), 256, 0, s>>>(src, (bf16*)dst, r, total);
+  else repack_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(src, (float*)dst, r, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
+                        int s, int C0, cudaStream_t st) {
+  const long long total = (long long)B * H * W * C0;
+  pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, H, W, s, C0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float* bias, void* out, bool is_bf16,
+                                     int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+  const long long total = (long long)B * H * W * Cout;
+  if (is_bf16) pointwise_in_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
+  else pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
+                                      int HW, float eps, cudaStream_t st) {
+  const int blocks = grid_for((long long)M * 32, 256, 148 * 8);
+  if (C <= 128) norm_film_kernel<T, 1><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  else if (C <= 256) norm_film_kernel<T, 2><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  else if (C <= 512) norm_film_kernel<T, 4><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  else if (C <= 1024) norm_film_kernel<T, 8><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  else if (C <= 2048) norm_film_kernel<T, 16><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  else return cudaErrorNotSupported;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_norm_film(const float* x, const float* film, const int* t_index, void* out, bool is_bf16, int M,
+                             int C, int HW, float eps, cudaStream_t st) {
+  if (C % 4 != 0) return cudaErrorNotSupported;
+  return is_bf16 ? norm_film_dispatch<bf16>(x, film, t_index, (bf16*)out, M, C, HW, eps, st)
+                 : norm_film_dispatch<float>(x, film, t_index, (float*)out, M, C, HW, eps, st);
+}
+
+cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool is_bf16, int n_t, int HW, int C,
+                             cudaStream_t st) {
+  const long long total = (long long)n_t * HW * 2 * C;
+  if (is_bf16) emb_build_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(pe, te, (bf16*)emb, n_t, HW, C);
+  else emb_build_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(pe, te, (float*)emb, n_t, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_cast(const float* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st) {
+  const long long total = (long long)B * (H / 2) * (W / 2) * C;
+  if (is_bf16) pool2_kernel<float, bf16><<<grid_for(total, 256), 256, 0, st>>>(x, (bf16*)out, B, H, W, C);
+  else pool2_kernel<float, float><<<grid_for(total, 256), 256, 0, st>>>(x, (float*)out, B, H, W, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_t(const void* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st) {
+  const long long total = (long long)B * (H / 2) * (W / 2) * C;
+  if (is_bf16) pool2_kernel<bf16, bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)out, B, H, W, C);
+  else pool2_kernel<float, float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cudaStream_t st) {
+  if (is_bf16) cast_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(x, (bf16*)out, n);
+  else cast_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(x, (float*)out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st) {
+  if (C % 4 != 0) return cudaErrorNotSupported;
+  const long long total = (long long)B * H * W * (C / 4);
+  upsample_add_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, ylow, B, H, W, C / 4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, bool is_bf16,
+                                    int B, int H, int W, int C, int head_dim, int win_h, int win_w, int shift,
+                                    cudaStream_t st) {
+  if (head_dim != 32 || win_h * win_w > 64) return cudaErrorNotSupported;
+  const int Hp = (H + win_h - 1) / win_h * win_h, Wp = (W + win_w - 1) / win_w * win_w;
+  dim3 grid(B * (Hp / win_h) * (Wp / win_w), C / head_dim);
+  if (grid.y > 65535u) return cudaErrorNotSupported;
+  if (is_bf16)
+    window_attention_kernel<bf16, 32><<<grid, 64, 0, st>>>((const bf16*)qkv, (const bf16*)xm, b_in, (bf16*)att, H, W, C,
+                                                          win_h, win_w, shift, Hp, Wp);
+  else
+    window_attention_kernel<float, 32><<<grid, 64, 0, st>>>((const float*)qkv, (const float*)xm, b_in, (float*)att, H, W,
+                                                           C, win_h, win_w, shift, Hp, Wp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_final(const float* x, const float* w, const float* bias, const float* xin, const float* noise,
+                         float* out, DdimScalars co, int B, int Cin, int H, int W, int s, int C0, cudaStream_t st) {
+  if (Cin * s * s > 32) return cudaErrorNotSupported;
+  const long long M = (long long)B * H * W;
+  final_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(x, w, bias, xin, noise, out, co, B, Cin, H, W, s, C0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* w, const float* bias,
+                                      const float* prev, float* out, uint8_t* out_u8, int B, int H, int W, int C,
+                                      int Cout, cudaStream_t st) {
+  if (Cout > 32) return cudaErrorNotSupported;
+  const long long M = (long long)B * H * W;
+  const unsigned grid = (unsigned)((M + 31) / 32);
+  if (is_bf16) pointwise_out_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+  else pointwise_out_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+  return cudaGetLastError();
+}

@@ -1,0 +1,464 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM 3x3 convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0     TMA producer  (one lane): A tile 128x64 + B tile BNx64 per stage, 128B-swizzled, mbarrier tx-count
+//   warp 1     MMA issuer    (one lane): 4 x tcgen05.mma (M128, N=BN, K16) per stage into one of two TMEM accumulators
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / activation / ReGLU gate / residual -> global
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue), so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+//
+// A operand modes: AM_ROWS  -- plain [M,K] row-major matrix (1x1 convolutions on NHWC activations)
+//                  AM_CONV3 -- NHWC tensor seen through a 4-d tensor map; the 9 taps are 9 shifted box loads whose
+//                              out-of-bounds elements TMA zero-fills (= the convolution's zero padding, vae.py:57-58)
+// Every mbarrier wait carries a watchdog: a stuck pipeline sets a fault flag and drains instead of hanging the GPU.
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcContext {
+  EncodeTiledFn encode;
+  int num_sms;
+  int* fault_dev;
+  int device;
+};
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 192;
+
+struct TcTiling {
+  int m_tiles, n_tiles, num_kb, total;
+  int TW, TH, TB;   // AM_CONV3: the 128-pixel tile is TB images x TH rows x TW columns
+};
+
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + 2 * BN * 4;
+};
+
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (true) {
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    if (*s_abort) return;
+    if (clock64() - t0 > 3000000000LL) {   // ~1.5 s at 2 GHz: pipeline is stuck, drain instead of hanging
+      *s_abort = 1;
+      atomicCAS(fault, 0, code);
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int AMODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
+               const TcTiling tl, int* fault) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    *s_abort = 0;
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_z = tl.m_tiles * tl.n_tiles;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+        const int z = t / tiles_per_z, rem = t % tiles_per_z;
+        const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        int b0 = 0, h0 = 0, w0 = 0;
+        if (AMODE == AM_CONV3) {
+          const int hw = d.cH * d.cW;
+          b0 = m0 / hw;
+          const int r = m0 % hw;
+          h0 = r / d.cW;
+          w0 = r % d.cW;
+        }
+        for (int kb = 0; kb < tl.num_kb; ++kb) {
+          wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
+          uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          const int kk = kb * BK;
+          if (AMODE == AM_ROWS) {
+            ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
+          } else {
+            const int tap = kk / d.cC, c0 = kk % d.cC;
+            ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+          }
+          int brow, bcol = kk;
+          if (d.sel == 2) { brow = d.sel_rows[kk / d.sel_span] + n0; bcol = kk % d.sel_span; }
+          else if (d.sel == 1) brow = d.sel_rows[n0 / d.sel_span] + n0 % d.sel_span;
+          else brow = n0;
+          ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow + (int)(z * d.w_row_b));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+        wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < tl.num_kb; ++kb) {
+          wait_bar(&full[stage], phase, s_abort, fault, 3);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty[stage]);        // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[as]);             // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrant warp%4)
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    uint32_t as = 0, aphase = 0;
+    for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+      const int z = t / tiles_per_z, rem = t % tiles_per_z;
+      const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
+      const int m0 = mt * BM, n0 = nt * BN;
+      float* sb = s_bias + as * BN;
+      for (int c = et; c < BN; c += 128) sb[c] = (n0 + c < d.N) ? bias_of_col(d, z, n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      wait_bar(&tfull[as], aphase, s_abort, fault, 4);
+      ptx::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < d.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= d.N) break;
+        uint32_t r[32];
+        if (d.epi == EPI_REGLU) {
+          if ((c >> 1) & 1) continue;            // b-chunk, consumed together with its a-chunk
+          uint32_t rb[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, r);
+          ptx::tmem_ld_32x32(t_row + c * 32 + 64, rb);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            const int j = (n >> 7) * 64 + (n & 127);
+            bf16* o = reinterpret_cast<bf16*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + j;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = __uint_as_float(r[2 * i]) + sb[c * 32 + 2 * i];
+              const float a1 = __uint_as_float(r[2 * i + 1]) + sb[c * 32 + 2 * i + 1];
+              const float g0 = fmaxf(__uint_as_float(rb[2 * i]) + sb[c * 32 + 64 + 2 * i], 0.f);
+              const float g1 = fmaxf(__uint_as_float(rb[2 * i + 1]) + sb[c * 32 + 64 + 2 * i + 1], 0.f);
+              pk[i] = pack_bf16(a0 * g0, a1 * g1);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<uint4*>(o)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+          continue;
+        }
+        ptx::tmem_ld_32x32(t_row + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[c * 32 + i];
+        const bool full_chunk = n + 32 <= d.N;
+        if (d.epi == EPI_ACCUM_F32) {
+          float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 cur = reinterpret_cast<float4*>(o)[i];
+              cur.x += v[4 * i]; cur.y += v[4 * i + 1]; cur.z += v[4 * i + 2]; cur.w += v[4 * i + 3];
+              reinterpret_cast<float4*>(o)[i] = cur;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i) if (n + i < d.N) o[i] += v[i];
+          }
+        } else if (d.epi == EPI_STORE_F32) {
+          float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 32; ++i) if (n + i < d.N) o[i] = v[i];
+          }
+        } else {   // EPI_STORE / EPI_CONVT: bf16 out
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+          bf16* o;
+          if (d.epi == EPI_CONVT) o = reinterpret_cast<bf16*>(d.out) + convt_offset(d, m, n);
+          else o = reinterpret_cast<bf16*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
+          if (full_chunk) {
+            if (d.res != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(d.res) + (long long)m * d.ldr + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(rp + i);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
+                  v[8 * i + 2 * k] += __low2float(h2);
+                  v[8 * i + 2 * k + 1] += __high2float(h2);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<uint4*>(o)[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                                          pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (n + i < d.N) {
+                float x = v[i];
+                if (d.res != nullptr) x += __bfloat162float(reinterpret_cast<const bf16*>(d.res)[(long long)m * d.ldr + n + i]);
+                o[i] = __float2bfloat16_rn(x);
+              }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+bool conv_tile(const GemmDesc& d, int& TW, int& TH, int& TB) {
+  const int W = d.cW, H = d.cH;
+  if (W >= 128) {
+    if (W % 128) return false;
+    TW = 128; TH = 1; TB = 1;
+    return true;
+  }
+  if (W <= 0 || (128 % W) != 0) return false;
+  TW = W;
+  const int rows = 128 / W;
+  if (H >= rows) {
+    if (H % rows) return false;
+    TH = rows; TB = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  TH = H; TB = rows / H;
+  return true;
+}
+
+int pick_bn(const GemmDesc& d, int num_sms) {
+  const int batch = d.batch > 0 ? d.batch : 1;
+  const long long m_tiles = (d.M + BM - 1) / BM;
+  auto ok = [&](int bn) {
+    if (d.N % bn != 0 && !(d.sel == 0 && d.epi != EPI_REGLU && bn == 64 && d.N % 32 == 0)) return false;
+    if (d.sel == 1 && d.sel_span % bn) return false;
+    if (d.epi == EPI_REGLU && bn < 128) return false;
+    return true;
+  };
+  if (ok(256) && m_tiles * (d.N / 256) * batch >= 2LL * num_sms) return 256;
+  if (ok(128)) return 128;
+  if (ok(256)) return 256;
+  if (ok(64)) return 64;
+  return 0;
+}
+
+}  // namespace
+
+bool tc_supported(const GemmDesc& d) {
+  if (d.K <= 0 || d.K % BK) return false;
+  if (d.ldw % 8) return false;
+  if (d.amode == AM_ROWS) {
+    if (d.lda % 8 || d.a_koff_b % 8) return false;
+  } else {
+    int a, b, c;
+    if (d.cC % BK || d.lda % 8 || d.a_koff_b % 8) return false;
+    if (!conv_tile(d, a, b, c)) return false;
+  }
+  if (d.sel == 2 && d.sel_span % BK) return false;
+  if (d.epi == EPI_REGLU && d.glu_chunk != 64) return false;
+  if (d.epi == EPI_CONVT && d.ctC % 32) return false;
+  if (d.epi != EPI_CONVT && (d.ldo % 8 || d.out_off_b % 8)) return false;
+  if (d.res && d.ldr % 8) return false;
+  if (d.N % 32) return false;
+  return pick_bn(d, 148) != 0;
+}
+
+TcContext* tc_context_create(int device, char* err, int errlen) {
+  TcContext* ctx = new TcContext();
+  ctx->device = device;
+  ctx->encode = nullptr;
+  ctx->fault_dev = nullptr;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    delete ctx;
+    return nullptr;
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { snprintf(err, errlen, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); delete ctx; return nullptr; }
+  if (prop.major != 10) {
+    snprintf(err, errlen, "device %d is sm_%d%d; libldmb200 is built for sm_100a only", device, prop.major, prop.minor);
+    delete ctx;
+    return nullptr;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  e = cudaMalloc(&ctx->fault_dev, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->fault_dev, 0, sizeof(int));
+  if (e != cudaSuccess) { snprintf(err, errlen, "cudaMalloc(fault flag): %s", cudaGetErrorString(e)); delete ctx; return nullptr; }
+  return ctx;
+}
+
+void tc_context_destroy(TcContext* ctx) {
+  if (!ctx) return;
+  if (ctx->fault_dev) cudaFree(ctx->fault_dev);
+  delete ctx;
+}
+
+int tc_read_fault(TcContext* ctx, cudaStream_t s) {
+  int v = 0;
+  if (cudaMemcpyAsync(&v, ctx->fault_dev, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  return v;
+}
+
+template <int BN, int AMODE>
+static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDesc& d,
+                                  const TcTiling& tl, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = tl.total < ctx->num_sms ? tl.total : ctx->num_sms;
+  gemm_tc_kernel<BN, AMODE><<<grid, kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, d, tl, ctx->fault_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
+  if (!tc_supported(d)) return cudaErrorNotSupported;
+  const int bn = pick_bn(d, ctx->num_sms);
+  const int batch = d.batch > 0 ? d.batch : 1;
+  TcTiling tl;
+  tl.m_tiles = (d.M + BM - 1) / BM;
+  tl.n_tiles = (d.N + bn - 1) / bn;
+  tl.num_kb = d.K / BK;
+  tl.total = tl.m_tiles * tl.n_tiles * batch;
+  tl.TW = tl.TH = tl.TB = 0;
+
+  CUtensorMap tmA, tmB;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (d.amode == AM_ROWS) {
+    // inner extent: every column reachable from this A (covers the batch k-offsets); rows = M
+    const cuuint64_t gdim[2] = {(cuuint64_t)d.lda, (cuuint64_t)d.M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)d.lda * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    r = ctx->encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.A), gdim, gstr, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    conv_tile(d, tl.TW, tl.TH, tl.TB);
+    const int Bimg = d.M / (d.cH * d.cW);
+    const cuuint64_t gdim[4] = {(cuuint64_t)d.lda, (cuuint64_t)d.cW, (cuuint64_t)d.cH, (cuuint64_t)Bimg};
+    const cuuint64_t gstr[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.lda * 2 * d.cW, (cuuint64_t)d.lda * 2 * d.cW * d.cH};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)tl.TW, (cuuint32_t)tl.TH, (cuuint32_t)tl.TB};
+    r = ctx->encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.A), gdim, gstr, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  {
+    // weight rows: everything reachable (stacked experts / batches); the epilogue guards columns >= N
+    long long rows = d.N;
+    if (d.sel == 1) { rows = 0; for (int q = 0; q < d.N / d.sel_span; ++q) if (d.sel_rows[q] + d.sel_span > rows) rows = d.sel_rows[q] + d.sel_span; }
+    if (d.sel == 2) { rows = 0; for (int q = 0; q < d.K / d.sel_span; ++q) if (d.sel_rows[q] + d.N > rows) rows = d.sel_rows[q] + d.N; }
+    rows += (long long)(batch - 1) * d.w_row_b;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d.ldw, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)d.ldw * 2};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    r = ctx->encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.W), gdim, gstr, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  if (d.amode == AM_ROWS) {
+    if (bn == 256) return launch_tc_inst<256, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
+    if (bn == 128) return launch_tc_inst<128, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
+    return launch_tc_inst<64, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
+  }
+  if (bn == 256) return launch_tc_inst<256, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
+  if (bn == 128) return launch_tc_inst<128, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
+  return launch_tc_inst<64, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
+}

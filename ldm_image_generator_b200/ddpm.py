@@ -1,0 +1,114 @@
+"""DDPM/DDIM sampler with the reference API (/root/reference/ddpm.py:10-93).
+
+``DDPM.sample`` keeps the reference's signature, seeding, timestep list, fp32 CPU noise
+schedule and torch-generator consumption; each iteration is ONE library call
+(``UNet.denoise_step`` -> ``ldmb_unet_forward`` with the DDIM scalars), the posterior update
+being fused into the UNet's last kernel.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+import torch.nn as nn
+from tqdm import tqdm
+
+from . import _lib
+from .unet import UNet
+
+_shared_default_unet = None
+
+
+def _default_model() -> UNet:
+    """The reference's default argument ``model=UNet()`` is evaluated once at import and shared by every
+    DDPM() (ddpm.py:16).  Same sharing here, but built on first use instead of at import."""
+    global _shared_default_unet
+    if _shared_default_unet is None:
+        _shared_default_unet = UNet()
+    return _shared_default_unet
+
+
+class DDPM(nn.Module):
+    # model(x=[B,...], time=[B], condition=None) -> eps
+    def __init__(self, model=None, beta_min=1e-4, beta_max=0.02, num_timesteps=1000, loss_function=nn.L1Loss(),
+                 lambda_max=20, lambda_min=-20):
+        super().__init__()
+        self.model = _default_model() if model is None else model
+        self.num_timesteps = num_timesteps
+        self.loss_function = loss_function
+        self.lambda_max, self.lambda_min = lambda_max, lambda_min
+        # Plain CPU fp32 tensors, not buffers: absent from state_dict and never moved by .to() (ddpm.py:19-37)
+        self.beta = torch.linspace(beta_min, beta_max, num_timesteps)
+        self.alpha = 1 - self.beta
+        self.alpha_bar = torch.Tensor([torch.prod(self.alpha[:t]) for t in range(1, num_timesteps + 1)])
+        tilde = [1]
+        for t in range(1, num_timesteps):
+            tilde.append((1 - self.alpha_bar[t - 1]) / (1 - self.alpha_bar[t]) * self.beta[t])
+        self.beta_tilde = torch.Tensor(tilde)
+
+    def calculate_loss(self, x, condition=None):
+        raise NotImplementedError("training (ddpm.py:39-48) is outside the sampling path this package implements")
+
+    def timesteps(self, num_steps=20, schedule="linear"):
+        """ddpm.py:66-72: the descending (t, t_next) pairs the loop visits."""
+        if schedule == "linear":
+            steps = list(torch.linspace(0, self.num_timesteps - 1, num_steps).int().numpy())
+        elif type(schedule) == list:
+            steps = schedule
+        else:
+            # the reference does `raise f"..."`, i.e. a TypeError at run time (ddpm.py:71)
+            raise TypeError(f"schedule \"{schedule}\" is not implemented.")
+        return list(zip(reversed(steps), reversed([0] + steps[:-1])))
+
+    def ddim_scalars(self, alpha_cum, t, t_next, eta):
+        """The per-step fp32 scalars, computed on the CPU exactly as ddpm.py:81-85 does."""
+        sigma = eta * torch.sqrt((1 - alpha_cum[t_next]) / (1 - alpha_cum[t])) * torch.sqrt(1 - alpha_cum[t] / alpha_cum[t_next])
+        co = _lib.DdimCoef()
+        co.c_eps_in = float(torch.sqrt(1 - alpha_cum[t]))
+        co.c_div = float(torch.sqrt(alpha_cum[t]))
+        co.c_x0 = float(torch.sqrt(alpha_cum[t_next]))
+        co.c_eps_out = float(torch.sqrt(1 - alpha_cum[t_next] - sigma ** 2))
+        co.sigma = float(sigma)
+        co.final_step = int(t == 0)
+        return co, sigma
+
+    # sample as DDIM (http://arxiv.org/abs/2010.02502)
+    @torch.no_grad()
+    def sample(self, x_shape=(1, 3, 64, 64), condition=None, seed=None, num_steps=20, use_autocast=True,
+               schedule="linear", eta=0, x_T=None, progress=True):
+        """Same contract as ddpm.py:52-93.  Extra keyword-only-in-spirit arguments:
+        ``x_T`` -- start from this tensor instead of ``torch.randn`` (CPU- vs GPU-generator parity,
+        SURVEY.md 8c rule 4); ``progress`` -- show the tqdm bar.
+        ``use_autocast`` is accepted for compatibility: arithmetic precision is the UNet's
+        ``precision`` ('bf16' default, 'fp32' validation), not an autocast context."""
+        device = next(self.model.parameters()).device
+        if seed != None:  # noqa: E711  (reference semantics: seed=0 seeds)
+            random.seed(seed)
+            torch.manual_seed(seed)
+            torch.cuda.manual_seed(seed)
+        x = torch.randn(*x_shape, device=device)
+        if x_T is not None:
+            x = x_T.to(device=device, dtype=torch.float32).clone()
+        pairs = self.timesteps(num_steps, schedule)
+        alpha_cum = torch.cumprod((1 - self.beta), dim=0)
+        fused = isinstance(self.model, UNet)
+        bar = tqdm(total=len(pairs), disable=not progress)
+        for t, t_next in pairs:
+            t, t_next = int(t), int(t_next)
+            co, sigma = self.ddim_scalars(alpha_cum, t, t_next, eta)
+            if fused:
+                # ddpm.py:78 then :80 -- the noise is drawn every step (even for eta=0) so the torch
+                # generator stays in lock-step with the reference across un-reseeded calls
+                e = torch.randn(*x_shape, device=device)
+                x = self.model.denoise_step(x, t, co, e if co.sigma != 0.0 else None)
+            else:
+                # foreign eps-model: generic host-side update, same operation order as ddpm.py:82-91
+                e_theta = self.model(x=x, time=torch.full((x_shape[0],), t, device=device), condition=None)
+                e = torch.randn(*x_shape, device=device)
+                x_t0 = (x - co.c_eps_in * e_theta) / co.c_div
+                x = x_t0 if t == 0 else co.c_x0 * x_t0 + co.c_eps_out * e_theta + co.sigma * e
+            if progress:
+                bar.set_description(f"t: {t}, sigma: {sigma}")
+            bar.update(1)
+        bar.close()
+        return x

@@ -1,0 +1,176 @@
+"""Thin object wrapper over the C ABI: one ``Handle`` per module instance per device.
+
+PyTorch is used here only as plumbing -- it owns the device tensors and the current
+stream; every arithmetic operator of the path runs inside libldmb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+PRECISIONS = {"bf16": _lib.BF16, "fp32": _lib.FP32_VALIDATE}
+
+
+class LdmbError(RuntimeError):
+    pass
+
+
+def default_precision() -> str:
+    p = os.environ.get("LDMB_PRECISION", "bf16").lower()
+    if p not in PRECISIONS:
+        raise ValueError(f"LDMB_PRECISION must be one of {sorted(PRECISIONS)}, got {p!r}")
+    return p
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise LdmbError(
+            f"{what} is on {t.device}: this implementation runs only on a CUDA device (sm_100a); "
+            "there is no CPU fallback. Move the module and its inputs to 'cuda'.")
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 contiguous view/copy (host code only; no arithmetic)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Handle:
+    def __init__(self, device: torch.device, precision: str):
+        if device.type != "cuda":
+            raise LdmbError(f"cannot create a libldmb200 handle on {device}: CUDA only, no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.precision = precision
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream()      # make sure the primary context exists before the library touches it
+        h = C.c_void_p()
+        rc = self.lib.ldmb_create(self.device.index, PRECISIONS[precision], C.byref(h))
+        if rc != 0 or not h:
+            raise LdmbError(f"ldmb_create(device={self.device.index}) failed with status {_lib.STATUS.get(rc, rc)} "
+                            "(needs an sm_100a GPU)")
+        self.h = h
+        self._param_keys: Dict[str, Tuple] = {}
+        self._keepalive = []
+
+    # ------------------------------------------------------------------ plumbing
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.ldmb_last_error(self.h)
+            raise LdmbError(f"libldmb200: {_lib.STATUS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.ldmb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.ldmb_launch_count(self.h))
+
+    def set_force_simt(self, on: bool) -> None:
+        self.check(self.lib.ldmb_set_force_simt(self.h, int(on)))
+
+    def device_fault(self) -> int:
+        return int(self.lib.ldmb_check_device_fault(self.h, stream_ptr(self.device)))
+
+    def sync_params(self, loader, items: Iterable[Tuple[str, torch.Tensor]]) -> int:
+        """Upload every state_dict entry whose storage or version changed since the last call."""
+        n = 0
+        st = stream_ptr(self.device)
+        for name, t in items:
+            key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+            if self._param_keys.get(name) == key:
+                continue
+            _require_cuda(t, f"parameter {name}")
+            src = f32c(t.detach())
+            shape = (C.c_int64 * max(src.dim(), 1))(*src.shape)
+            self.check(loader(name.encode(), src.data_ptr(), shape, src.dim(), st))
+            self._param_keys[name] = key
+            n += 1
+        return n
+
+    # ------------------------------------------------------------------ UNet
+    def unet_configure(self, input_channels: int, stages: Sequence[int], channels: Sequence[int], stem_size: int) -> None:
+        cfg = _lib.UNetConfig()
+        cfg.input_channels, cfg.num_levels, cfg.stem_size = input_channels, len(stages), stem_size
+        if len(stages) > _lib.LDMB_MAX_LEVELS or len(stages) != len(channels):
+            raise LdmbError("stages/channels must have equal length <= 8")
+        for i, (b, c) in enumerate(zip(stages, channels)):
+            cfg.blocks[i], cfg.channels[i] = int(b), int(c)
+        self.check(self.lib.ldmb_unet_configure(self.h, C.byref(cfg)))
+
+    def unet_load(self, items) -> int:
+        return self.sync_params(lambda *a: self.lib.ldmb_unet_load_param(self.h, *a), items)
+
+    def unet_set_position_table(self, level: int, pe_chw: torch.Tensor) -> None:
+        pe = f32c(pe_chw.cpu())
+        Cc, Hl, Wl = pe.shape
+        self.check(self.lib.ldmb_unet_set_position_table(self.h, level, pe.data_ptr(), Cc, Hl, Wl, stream_ptr(self.device)))
+
+    def unet_forward(self, x: torch.Tensor, out: torch.Tensor, t_index, te_tables: Sequence[torch.Tensor], plan,
+                     coef: Optional[_lib.DdimCoef] = None, noise: Optional[torch.Tensor] = None) -> None:
+        B, _, H, W = x.shape
+        n_t = te_tables[0].shape[0]
+        ti = (C.c_int32 * B)(*t_index)
+        te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
+        flat = [int(v) for row in plan for v in row]
+        pl = (C.c_int32 * len(flat))(*flat)
+        self.check(self.lib.ldmb_unet_forward(
+            self.h, x.data_ptr(), out.data_ptr(), B, H, W, ti, n_t, te_ptrs, pl,
+            C.byref(coef) if coef is not None else None,
+            noise.data_ptr() if noise is not None else None, stream_ptr(self.device)))
+
+    # ------------------------------------------------------------------ VAE
+    def vae_configure(self, which: int, image_channels: int, latent_channels: int, channels: Sequence[int],
+                      stages: Sequence[int]) -> None:
+        cfg = _lib.VaeConfig()
+        cfg.image_channels, cfg.latent_channels, cfg.num_levels = image_channels, latent_channels, len(channels)
+        if len(channels) > _lib.LDMB_MAX_LEVELS or len(stages) != len(channels):
+            raise LdmbError("stages/channels must have equal length <= 8")
+        for i, (c, b) in enumerate(zip(channels, stages)):
+            cfg.channels[i], cfg.blocks[i] = int(c), int(b)
+        self.check(self.lib.ldmb_vae_configure(self.h, which, C.byref(cfg)))
+
+    def vae_load(self, which: int, items) -> int:
+        return self.sync_params(lambda *a: self.lib.ldmb_vae_load_param(self.h, which, *a), items)
+
+    def vae_decode(self, z: torch.Tensor, img: Optional[torch.Tensor], img_u8: Optional[torch.Tensor]) -> None:
+        B, _, hl, wl = z.shape
+        self.check(self.lib.ldmb_vae_decode(self.h, z.data_ptr(), img.data_ptr() if img is not None else None,
+                                            img_u8.data_ptr() if img_u8 is not None else None, B, hl, wl,
+                                            stream_ptr(self.device)))
+
+    def vae_encode(self, img: torch.Tensor, z: torch.Tensor) -> None:
+        B, _, H, W = img.shape
+        self.check(self.lib.ldmb_vae_encode(self.h, img.data_ptr(), z.data_ptr(), B, H, W, stream_ptr(self.device)))
+
+    # ------------------------------------------------------------------ kernel-level (tests / bench)
+    def gemm(self, A, Wt, bias, out, M, N, K, out_f32=0, act=0, force_simt=False) -> None:
+        self.check(self.lib.ldmb_gemm(self.h, A.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                      out.data_ptr(), M, N, K, out_f32, act, int(force_simt), stream_ptr(self.device)))
+
+    def conv3x3(self, x, Wt, bias, out, B, H, W, Cc, N, act=0, force_simt=False) -> None:
+        self.check(self.lib.ldmb_conv3x3(self.h, x.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                         out.data_ptr(), B, H, W, Cc, N, act, int(force_simt), stream_ptr(self.device)))
+
+    def channelnorm_film(self, x, film, out, M, Cc, HW) -> None:
+        self.check(self.lib.ldmb_channelnorm_film(self.h, x.data_ptr(), film.data_ptr(), out.data_ptr(), M, Cc, HW,
+                                                  stream_ptr(self.device)))

@@ -1,0 +1,172 @@
+"""UNet with the reference constructor / forward / state_dict contract
+(/root/reference/unet.py:9-103), executed by libldmb200.so.
+
+``UNet.forward(x, time, condition=None)`` makes ONE C-ABI call (``ldmb_unet_forward``) that
+runs the whole network on the current CUDA stream.  Host code here only
+  * draws the Python-``random`` decisions of the step in the reference's order
+    (stochastic depth unet.py:39, expert picks modules.py:35) into a plan,
+  * evaluates the (t)-only and (h,w)-only sinusoid tables (sinusoidal.py) on the host,
+  * keeps the library's repacked weight arena in sync with the nn.Parameters.
+"""
+from __future__ import annotations
+
+import random
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, runtime
+from .attention import CrossAttention, WindowAttention
+from .modules import ChannelNorm, RandomMoE, _FusedIntoUNet
+from .sinusoidal import PositionalEncoding2d, TimeEncoding2d
+
+
+class Encodings(_FusedIntoUNet):
+    """Time + position FiLM (unet.py:9-23).  Depends on (t, h, w) only, so the library evaluates
+    the MLP once per call for all images instead of once per image."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.proj1 = nn.Conv2d(channels * 2, channels * 4, 1, 1, 0)
+        self.act = nn.ReLU()
+        self.proj2 = nn.Conv2d(channels * 4, channels * 2, 1, 1, 0)
+        self.pe = PositionalEncoding2d(channels, return_encoding_only=True)
+        self.te = TimeEncoding2d(channels, return_encoding_only=True)
+
+
+class SwinBlock(_FusedIntoUNet):
+    def __init__(self, channels, head_dim=32, window_size=6, shift=0, attention=True, stochastic_depth=0.25):
+        super().__init__()
+        if head_dim != 32 or window_size != 6:
+            raise runtime.LdmbError("libldmb200 implements SwinBlock as the reference instantiates it: head_dim=32, window 6")
+        self.norm = ChannelNorm(channels)
+        self.ffn = RandomMoE(channels)
+        self.conv = nn.Conv2d(channels, channels, 3, 1, 1, groups=channels // head_dim)
+        self.stochastic_depth = stochastic_depth
+        self.attention_flag = attention
+        if attention:
+            self.self_attention = WindowAttention(channels, n_heads=channels // head_dim, window_size=window_size, shift=shift)
+            self.cross_attention = CrossAttention(channels, n_heads=channels // head_dim)
+        self.encodings = Encodings(channels)
+        self.shift = shift
+
+
+class SwinStack(_FusedIntoUNet):
+    def __init__(self, channels, head_dim=32, window_size=6, num_blocks=2, attention=True):
+        super().__init__()
+        blocks = []
+        for i in range(num_blocks):
+            blocks.append(SwinBlock(channels, head_dim, window_size,
+                                    shift=window_size // 2 if i % 2 == 0 else 0,
+                                    attention=attention and i >= num_blocks - 2))   # unet.py:55-60
+        self.blocks = nn.ModuleList(blocks)
+
+
+class UNetBlock(nn.Module):
+    def __init__(self, stage, ch_conv):
+        super().__init__()
+        self.stage = stage
+        self.ch_conv = ch_conv
+
+
+class UNet(nn.Module):
+    def __init__(self, input_channels=8, stages=[3, 3, 9, 3], channels=[128, 256, 512, 1024], stem_size=1):
+        super().__init__()
+        self.input_channels, self.stem_size = input_channels, stem_size
+        self.stage_blocks, self.stage_channels = list(stages), list(channels)
+        self.encoder_first = nn.Conv2d(input_channels, channels[0], stem_size, stem_size, 0)
+        self.decoder_last = nn.ConvTranspose2d(channels[0], input_channels, stem_size, stem_size, 0)
+        self.encoder_stages = nn.ModuleList([])
+        self.decoder_stages = nn.ModuleList([])
+        last = len(stages) - 1
+        for i, (n, c) in enumerate(zip(stages, channels)):
+            # same construction order as unet.py:80-87 so a torch seed yields the reference's initial weights
+            enc = SwinStack(c, num_blocks=n, attention=False)
+            down = nn.Identity() if i == last else nn.Sequential(nn.Conv2d(c, channels[i + 1], 1, 1, 0), nn.AvgPool2d(kernel_size=2))
+            dec = SwinStack(c, num_blocks=n)
+            up = nn.Identity() if i == last else nn.Sequential(nn.Upsample(scale_factor=2), nn.Conv2d(channels[i + 1], c, 1, 1, 0))
+            self.encoder_stages.append(UNetBlock(enc, down))
+            self.decoder_stages.insert(0, UNetBlock(dec, up))     # deepest first (unet.py:87)
+        self.precision = runtime.default_precision()
+        self._handle: Optional[runtime.Handle] = None
+        self._pe_res = None
+
+    # ------------------------------------------------------------------ host-side helpers
+    def set_precision(self, precision: str) -> "UNet":
+        """'bf16' (tcgen05 path) or 'fp32' (CUDA-core validation mode)."""
+        if precision not in runtime.PRECISIONS:
+            raise ValueError(precision)
+        if precision != self.precision:
+            self.precision, self._handle, self._pe_res = precision, None, None
+        return self
+
+    def blocks_in_execution_order(self) -> List[SwinBlock]:
+        out = []
+        for st in list(self.encoder_stages) + list(self.decoder_stages):
+            out.extend(st.stage.blocks)
+        return out
+
+    def draw_plan(self) -> List[Sequence[int]]:
+        """Consume Python's ``random`` exactly like one reference forward: per block, ``random.random()``
+        iff the block is in training mode (unet.py:39), then ``random.sample`` of 2 of the 4 experts
+        (modules.py:35) unless skipped."""
+        plan = []
+        for blk in self.blocks_in_execution_order():
+            if blk.training and random.random() <= blk.stochastic_depth:
+                plan.append((1, 0, 0))
+                continue
+            e1, e2 = random.sample(range(len(blk.ffn.experts)), 2)
+            plan.append((0, e1, e2))
+        return plan
+
+    def _prepare(self, device: torch.device) -> runtime.Handle:
+        h = self._handle
+        if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
+            h = runtime.Handle(device, self.precision)
+            h.unet_configure(self.input_channels, self.stage_blocks, self.stage_channels, self.stem_size)
+            self._handle, self._pe_res = h, None
+        h.unet_load(self.state_dict(keep_vars=True).items())
+        return h
+
+    def _run(self, x: torch.Tensor, t_values: Sequence[int], coef=None, noise=None, out=None, plan=None) -> torch.Tensor:
+        runtime._require_cuda(x, "UNet input")
+        p0 = next(self.parameters())
+        runtime._require_cuda(p0, "UNet parameters")
+        if x.dim() != 4 or x.shape[1] != self.input_channels:
+            raise RuntimeError(f"expected input[{', '.join(map(str, x.shape))}] to have {self.input_channels} channels, "
+                               f"but got {x.shape[1] if x.dim() == 4 else '?'} channels instead")
+        x = runtime.f32c(x)
+        with torch.cuda.device(x.device):
+            h = self._prepare(x.device)
+            B, _, H, W = x.shape
+            Hs, Ws = H // self.stem_size, W // self.stem_size
+            if self._pe_res != (Hs, Ws):
+                for lvl, c in enumerate(self.stage_channels):
+                    h.unet_set_position_table(lvl, self.encoder_stages[lvl].stage.blocks[0].encodings.pe.table(Hs >> lvl, Ws >> lvl))
+                self._pe_res = (Hs, Ws)
+            uniq = sorted(set(int(v) for v in t_values))
+            index = {v: i for i, v in enumerate(uniq)}
+            tt = torch.tensor(uniq, dtype=torch.long)
+            te = [self.encoder_stages[lvl].stage.blocks[0].encodings.te.table(tt) for lvl in range(len(self.stage_channels))]
+            if plan is None:
+                plan = self.draw_plan()
+            if out is None:
+                out = torch.empty_like(x)
+            h.unet_forward(x, out, [index[int(v)] for v in t_values], te, plan, coef, noise)
+        return out
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x, time, condition=None):
+        """eps = UNet(x, time).  ``condition`` is accepted and ignored, as in the reference
+        (unet.py:93,101 never pass it to the stages)."""
+        t_values = [int(v) for v in time.detach().reshape(-1).tolist()]
+        if len(t_values) == 1 and x.shape[0] > 1:
+            t_values = t_values * x.shape[0]
+        return self._run(x, t_values)
+
+    def denoise_step(self, x: torch.Tensor, t: int, coef: "_lib.DdimCoef", noise: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One iteration of DDPM.sample (ddpm.py:77-91): eps = UNet(x, t) and the DDIM update fused
+        into the network's last kernel.  Writes into ``out`` (default: in place into ``x``)."""
+        return self._run(x, [int(t)] * x.shape[0], coef=coef, noise=noise, out=x if out is None else out)

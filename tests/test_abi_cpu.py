@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/ldmb.h declares; host-side
+module API mirrors the reference's (state_dict layout, seeded init, schedule tables).  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ldm_image_generator_b200 import _lib, build
+    build.build_library()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from ldm_image_generator_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ldmb.h")).read()
+    declared = set(re.findall(r"\b(ldmb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ldmb_abi_version() == 1
+
+
+def test_create_fails_loudly_without_a_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    assert lib.ldmb_create(0, 0, ctypes.byref(h)) != 0 and not h
+    from ldm_image_generator_b200 import UNet, runtime
+    m = UNet(3, [1], [32])
+    with pytest.raises(runtime.LdmbError):
+        m(torch.zeros(1, 3, 8, 8), torch.zeros(1, dtype=torch.long))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ldm_image_generator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle"
+
+
+def test_module_api_layout_matches_oracle_key_templates():
+    """Constructor signatures + state_dict layout of the drop-in modules."""
+    from ldm_image_generator_b200 import DDPM, Decoder, Encoder, UNet
+    from oracle import restate as R
+    cfg = R.UNetCfg(input_channels=8, stages=(1, 2, 2), channels=(32, 64, 128))
+    sd = R.make_unet_state(cfg, 7)
+    m = UNet(cfg.input_channels, list(cfg.stages), list(cfg.channels), cfg.stem_size)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    m.load_state_dict(sd, strict=True)
+    d = DDPM(model=m)
+    assert all(k.startswith("model.") for k in d.state_dict()) and len(d.state_dict()) == len(sd)
+    assert {k: tuple(v.shape) for k, v in Decoder().state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in R.make_decoder_state(R.DecoderCfg()).items()}
+    assert {k: tuple(v.shape) for k, v in Encoder().state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in R.make_encoder_state(R.EncoderCfg()).items()}
+
+
+def test_host_schedule_is_bit_exact():
+    from ldm_image_generator_b200 import DDPM, UNet
+    from oracle import restate as R
+    d = DDPM(model=UNet(3, [1], [32]))
+    fix = torch.load(os.path.join(ROOT, "tests", "golden", "schedule.pt"))
+    assert torch.equal(d.beta, fix["beta"])
+    assert torch.equal(torch.cumprod(1 - d.beta, dim=0), fix["alpha"])
+    for n in (20, 50, 1000):
+        assert [(int(a), int(b)) for a, b in d.timesteps(n)] == R.step_pairs(R.linear_steps(1000, n))
+    assert d.timesteps(3, [5, 9, 100]) == [(100, 9), (9, 5), (5, 0)]
+    with pytest.raises(TypeError):
+        d.timesteps(3, "cosine")
+    co, sigma = d.ddim_scalars(fix["alpha"], 999, 978, 0)
+    want = R.ddim_coefficients(fix["alpha"], 999, 978, 0.0)
+    for k in ("c_eps_in", "c_div", "c_x0", "c_eps_out", "sigma"):
+        assert getattr(co, k) == float(want[k])
+
+
+def test_host_plan_and_tables_match_oracle():
+    import random
+    from ldm_image_generator_b200 import UNet
+    from ldm_image_generator_b200.sinusoidal import position_table, time_table
+    from oracle import restate as R
+    m = UNet()
+    for training in (False, True):
+        m.train(training)
+        random.seed(0); a = m.draw_plan(); sa = random.getstate()
+        random.seed(0); b = R.draw_plan(36, training)
+        assert [tuple(p) for p in a] == b and random.getstate() == sa
+    assert torch.equal(position_table(128, 32, 32), R.position_table(128, 32, 32))
+    t = torch.tensor([0, 20, 999])
+    assert torch.equal(time_table(256, t), R.time_table(256, t))

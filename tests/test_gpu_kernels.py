@@ -1,0 +1,114 @@
+"""GPU: single kernels through the C ABI against a plain torch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handles():
+    from ldm_image_generator_b200 import runtime
+    dev = torch.device("cuda", 0)
+    return {"bf16": runtime.Handle(dev, "bf16"), "fp32": runtime.Handle(dev, "fp32")}
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (1000, 384, 512), (4096, 768, 128), (130, 64, 64), (512, 96, 192),
+               (16, 1024, 1024), (8192, 256, 1536), (1024, 3072, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_fp32_validation_kernel(handles, M, N, K):
+    h = handles["fp32"]
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g); W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    h.gemm(A, W, b, out, M, N, K)
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    assert _rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("mode", ["store_bf16_relu", "store_f32", "accum_f32_leaky_none"])
+def test_gemm_tcgen05_matches_fp32_reference(handles, M, N, K, mode):
+    """bf16 operands, fp32 accumulate: must agree with an fp32 GEMM of the same bf16-rounded operands
+    to fp32 accumulation noise (store_f32) or bf16 output rounding (store_bf16)."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ W.double().t() + b.double()
+    if mode == "store_bf16_relu":
+        out = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        h.gemm(A, W, b, out, M, N, K, out_f32=0, act=1)
+        assert _rel(out.float(), ref.clamp_min(0)) < 4e-3
+        sim = torch.empty_like(out)
+        h.gemm(A, W, b, sim, M, N, K, out_f32=0, act=1, force_simt=True)
+        assert _rel(out.float(), sim.float()) < 4e-3
+    elif mode == "store_f32":
+        out = torch.full((M, N), 7.0, device="cuda")
+        h.gemm(A, W, b, out, M, N, K, out_f32=1)
+        assert _rel(out, ref) < 1e-5
+    else:
+        base = torch.randn(M, N, device="cuda", generator=g)
+        out = base.clone()
+        h.gemm(A, W, b, out, M, N, K, out_f32=2)
+        assert _rel(out, ref + base.double()) < 1e-5
+    assert h.device_fault() == 0
+
+
+CONV_SHAPES = [(2, 32, 32, 64, 64), (1, 8, 8, 128, 128), (2, 16, 16, 64, 128), (1, 128, 128, 64, 64),
+               (3, 64, 64, 128, 256), (5, 4, 4, 64, 64), (1, 256, 256, 64, 64), (2, 32, 32, 512, 512)]
+
+
+def _pack_conv(w):   # [N, C, 3, 3] -> [N, tap*C + c]
+    N, Cc = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(N, 9 * Cc).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,C,N", CONV_SHAPES)
+def test_conv3x3_tcgen05_implicit_gemm(handles, B, H, W, C, N):
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(B + H + C + N)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((B, H, W, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    h.conv3x3(x, _pack_conv(w), b, out, B, H, W, C, N, act=2)
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1), 0.01).permute(0, 2, 3, 1)
+    assert _rel(out.float(), ref) < 4e-3
+    assert h.device_fault() == 0
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 12, 20, 24, 40), (1, 7, 5, 8, 8)])
+def test_conv3x3_fp32_validation_kernel(handles, B, H, W, C, N):
+    h = handles["fp32"]
+    x = torch.randn(B, H, W, C, device="cuda"); w = torch.randn(N, C, 3, 3, device="cuda") / (9 * C) ** 0.5
+    b = torch.randn(N, device="cuda")
+    out = torch.empty(B, H, W, N, device="cuda")
+    h.conv3x3(x, _pack_conv(w), b, out, B, H, W, C, N)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()
+    assert _rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("C", [32, 128, 512, 1024, 2048])
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_channelnorm_film(handles, C, prec):
+    """modules.py:23-25 + unet.py:22 on NHWC rows."""
+    h = handles[prec]
+    M, HW = 4 * 37, 37
+    x = torch.randn(M, C, device="cuda") * 3 + 1
+    film = torch.randn(HW, 2 * C, device="cuda")
+    out = torch.empty(M, C, device="cuda", dtype=torch.bfloat16 if prec == "bf16" else torch.float32)
+    h.channelnorm_film(x, film, out, M, C, HW)
+    xn = (x - x.mean(1, keepdim=True)) / torch.sqrt(x.var(1, keepdim=True) + 1e-4)
+    idx = torch.arange(M, device="cuda") % HW
+    ref = xn * film[idx, :C] + film[idx, C:]
+    assert _rel(out.float(), ref) < (4e-3 if prec == "bf16" else 2e-6)

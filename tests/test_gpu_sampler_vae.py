@@ -1,0 +1,122 @@
+"""GPU parity of the DDIM sampler (ddpm.py:51-93) and of the VAE decode/encode (vae.py)."""
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle.gen_golden import DECODER_CASES, ENCODER_CASES, UNET_CASES
+from tests.gpu_util import PSNR_MIN_DB, assert_no_fault, build_decoder, build_encoder, build_unet, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _ddpm(precision):
+    from ldm_image_generator_b200 import DDPM
+    kw, wseed, B, H, W = UNET_CASES["unet_tiny"]
+    cfg = R.UNetCfg(**kw)
+    return DDPM(model=build_unet(cfg, R.make_unet_state(cfg, wseed), precision)), (B, cfg.input_channels, H, W)
+
+
+def test_sampler_fp32_matches_reference_fixture():
+    """Whole DDPM.sample trajectories (eval and train mode, linear and list schedules) against the reference's
+    own output; x_T is the CPU-generator draw the reference made (SURVEY 8c rule 4)."""
+    d, shape = _ddpm("fp32")
+    fix = golden("ddim_tiny")
+    for mode, training in (("eval", False), ("train", True)):
+        d.train(training)
+        x0 = d.sample(shape, seed=11, num_steps=8, use_autocast=False, x_T=fix["x_T"], progress=False).cpu()
+        err = R.rel_l2(x0, fix["x0_" + mode])
+        print("sampler fp32", mode, err)
+        assert err < 2e-4, (mode, err)      # 8 steps through the 1/sqrt(abar_999)=157x amplification
+    d.eval()
+    x0 = d.sample(shape, seed=11, num_steps=6, use_autocast=False, schedule=[0, 40, 80, 120, 160, 199],
+                  x_T=fix["x_T"], progress=False).cpu()
+    assert R.rel_l2(x0, fix["x0_eval_lowt"]) < 2e-5
+    assert_no_fault(d.model)
+
+
+def test_sampler_bf16_conditioned_trajectory():
+    d, shape = _ddpm("bf16")
+    fix = golden("ddim_tiny")
+    d.eval()
+    x0 = d.sample(shape, seed=11, num_steps=6, schedule=[0, 40, 80, 120, 160, 199], x_T=fix["x_T"], progress=False).cpu()
+    err = R.rel_l2(x0, fix["x0_eval_lowt"])
+    print("sampler bf16 low-t", err)
+    assert err < 2e-2
+
+
+def test_sampler_torch_generator_lockstep_and_eta():
+    """eta > 0: the per-step noise comes from torch's CUDA generator exactly where the reference draws it
+    (one randn for x_T, one per step), so two identically seeded calls agree and the generator advances
+    by the same amount whether or not eta is 0."""
+    d, shape = _ddpm("fp32")
+    d.eval()
+    a = d.sample(shape, seed=3, num_steps=4, eta=0.5, progress=False)
+    b = d.sample(shape, seed=3, num_steps=4, eta=0.5, progress=False)
+    assert torch.equal(a, b)
+    torch.manual_seed(9); torch.cuda.manual_seed(9)
+    d.sample(shape, seed=None, num_steps=4, eta=0.0, progress=False)
+    after = torch.randn(4, device="cuda")
+    torch.manual_seed(9); torch.cuda.manual_seed(9)
+    for _ in range(5):
+        torch.randn(*shape, device="cuda")
+    assert torch.equal(after, torch.randn(4, device="cuda"))
+    # and eta > 0 matches the oracle's update when fed the same noises
+    import random
+    torch.manual_seed(3); torch.cuda.manual_seed(3)
+    xT = torch.randn(*shape, device="cuda")
+    noises = [torch.randn(*shape, device="cuda").cpu() for _ in range(4)]
+    kw, wseed, *_ = UNET_CASES["unet_tiny"]
+    cfg = R.UNetCfg(**kw)
+    want = R.ddim_sample(R.make_unet_state(cfg, wseed), cfg, xT.cpu(), R.linear_steps(1000, 4), False, py_seed=3,
+                         eta=0.5, noises=noises)
+    assert R.rel_l2(a.cpu(), want) < 2e-4
+
+
+@pytest.mark.parametrize("name", sorted(DECODER_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decoder_matches_reference_fixture(name, precision):
+    kw, wseed, *_ = DECODER_CASES[name]
+    cfg = R.DecoderCfg(**kw)
+    fix = golden(name)
+    dec = build_decoder(cfg, R.make_decoder_state(cfg, wseed), precision)
+    with torch.no_grad():
+        y = dec(fix["z"].cuda()).cpu()
+        u8 = dec.decode_to_uint8(fix["z"].cuda()).cpu()
+    err, db = R.rel_l2(y, fix["y"]), R.psnr(y.clamp(-1, 1), fix["y"].clamp(-1, 1))
+    print(f"{name} {precision}: rel-L2 {err:.3e} PSNR {db:.1f} dB")
+    assert err < (1e-5 if precision == "fp32" else 1e-2)
+    assert db >= PSNR_MIN_DB
+    want = R.to_uint8_image(fix["y"])
+    diff = (u8.int() - want.int()).abs()
+    assert int(diff.max()) <= (1 if precision == "fp32" else 3)
+    if precision == "fp32":
+        assert float((diff == 0).float().mean()) > 0.995      # truncation boundaries only
+    assert_no_fault(dec)
+
+
+@pytest.mark.parametrize("name", sorted(ENCODER_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_encoder_matches_reference_fixture(name, precision):
+    kw, wseed, *_ = ENCODER_CASES[name]
+    cfg = R.EncoderCfg(**kw)
+    fix = golden(name)
+    enc = build_encoder(cfg, R.make_encoder_state(cfg, wseed), precision)
+    with torch.no_grad():
+        z = enc(fix["x"].cuda()).cpu()
+    err = R.rel_l2(z, fix["y"])
+    print(f"{name} {precision}: rel-L2 {err:.3e}")
+    assert err < (1e-5 if precision == "fp32" else 1.5e-2)
+    assert_no_fault(enc)
+
+
+def test_vae_roundtrip_shapes_and_wrapper():
+    from ldm_image_generator_b200 import VAE
+    ec, dc = R.EncoderCfg(channels=(8, 16, 32, 64)), R.DecoderCfg(channels=(64, 32, 16, 8))
+    vae = VAE(build_encoder(ec, R.make_encoder_state(ec, 5), "fp32"), build_decoder(dc, R.make_decoder_state(dc, 5), "fp32"))
+    x = torch.randn(2, 3, 32, 48, device="cuda").clamp(-1, 1)
+    z = vae.encode(x)
+    assert tuple(z.shape) == (2, 8, 4, 6)
+    y = vae.decode(z)
+    assert tuple(y.shape) == (2, 3, 32, 48)
+    want = R.decoder_forward(R.make_decoder_state(dc, 5), dc, R.encoder_forward(R.make_encoder_state(ec, 5), ec, x.cpu()))
+    assert R.rel_l2(y.cpu(), want) < 1e-5

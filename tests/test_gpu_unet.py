@@ -1,0 +1,82 @@
+"""GPU parity of the UNet step: CUDA path through the drop-in module API vs the reference's output
+(committed fixtures made from the unmodified reference) and vs the CPU oracle on fresh inputs."""
+import random
+
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle.gen_golden import UNET_CASES
+from tests.gpu_util import BF16_STEP_TOL, FP32_STEP_TOL, assert_no_fault, build_unet, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, x, t, plan):
+    with torch.no_grad():
+        return model._run(x.cuda(), [int(v) for v in t], plan=plan).cpu()
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_pixel3", "unet_mid", "unet_default"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_step_matches_reference_fixture(name, precision):
+    kw, wseed, B, H, W = UNET_CASES[name]
+    cfg = R.UNetCfg(**kw)
+    fix = golden(name)
+    model = build_unet(cfg, R.make_unet_state(cfg, wseed), precision)
+    tol = FP32_STEP_TOL if precision == "fp32" else BF16_STEP_TOL
+    for mode in ("eval", "train"):
+        plan = [tuple(int(v) for v in row) for row in fix["plan_" + mode]]
+        y = _run(model, fix["x"], fix["t"], plan)
+        err = R.rel_l2(y, fix["y_" + mode])
+        print(f"{name} {precision} {mode}: rel-L2 {err:.3e}")
+        assert err < tol, (name, precision, mode, err)
+    assert_no_fault(model)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_forward_api_consumes_python_rng_in_lockstep(precision):
+    """UNet.forward(x=, time=, condition=) draws the stochastic-depth / expert decisions from Python's
+    random stream exactly as the reference (unet.py:39, modules.py:35)."""
+    cfg = R.UNetCfg(input_channels=8, stages=(1, 2, 2), channels=(32, 64, 128))
+    sd = R.make_unet_state(cfg, 7)
+    model = build_unet(cfg, sd, precision)
+    x = torch.randn(3, 8, 16, 24); t = torch.tensor([999, 3, 500])
+    for training in (False, True):
+        model.train(training)
+        random.seed(21)
+        with torch.no_grad():
+            y = model(x=x.cuda(), time=t.cuda(), condition=None).cpu()
+        after = random.getstate()
+        random.seed(21)
+        plan = R.draw_plan(len(R.block_table(cfg)), training)
+        assert random.getstate() == after
+        err = R.rel_l2(y, R.unet_forward(sd, cfg, x, t, plan))
+        assert err < (FP32_STEP_TOL if precision == "fp32" else BF16_STEP_TOL), err
+
+
+def test_unet_real_widths_nonsquare_batch_vs_oracle():
+    """Real channel widths (tcgen05 path), non-square latent, per-sample timesteps, train-mode skips."""
+    cfg = R.UNetCfg(input_channels=8, stages=(2, 2), channels=(128, 256))
+    sd = R.make_unet_state(cfg, 31)
+    x = torch.randn(3, 8, 20, 28); t = torch.tensor([10, 999, 10])
+    random.seed(5)
+    plan = R.draw_plan(len(R.block_table(cfg)), True)
+    want = R.unet_forward(sd, cfg, x, t, plan)
+    for precision, tol in (("fp32", FP32_STEP_TOL), ("bf16", BF16_STEP_TOL)):
+        model = build_unet(cfg, sd, precision)
+        err = R.rel_l2(_run(model, x, t, plan), want)
+        print(f"nonsquare {precision}: {err:.3e}")
+        assert err < tol
+        assert_no_fault(model)
+
+
+def test_bad_inputs_raise_like_the_reference():
+    cfg = R.UNetCfg(input_channels=8, stages=(1, 1), channels=(32, 64))
+    model = build_unet(cfg, R.make_unet_state(cfg, 1), "fp32")
+    with pytest.raises(RuntimeError):      # channel mismatch: conv error in the reference (sample_ddpm.py:36 at defaults)
+        model(torch.zeros(1, 3, 8, 8, device="cuda"), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError):      # odd resolution: skip/upsample size mismatch in the reference (unet.py:101)
+        model(torch.zeros(1, 8, 9, 9, device="cuda"), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError):      # no CPU fallback
+        model(torch.zeros(1, 8, 8, 8), torch.zeros(1, dtype=torch.long))
