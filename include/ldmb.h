@@ -102,6 +102,15 @@ int64_t ldmb_launch_count(const ldmb_handle* h);
 /* 0, or the watchdog code a tcgen05 pipeline wrote when an mbarrier wait timed out (device read; synchronises). */
 int ldmb_check_device_fault(ldmb_handle* h, void* stream);
 
+/* Per-kernel-class device timing for roofline reports (bench.py).  Between begin and end every launch is
+ * bracketed by CUDA events on its stream; end synchronises and returns, per class, the summed event time (ms),
+ * the summed algorithmic work (FLOPs for the GEMM/conv classes, bytes for the HBM-bound ones) and the launch count.
+ * Classes: 0 tcgen05 GEMM, 1 tcgen05 3x3 conv, 2 CUDA-core GEMM/conv, 3 ChannelNorm+FiLM, 4 window attention, 5 other.
+ * Arrays must hold LDMB_PROFILE_CLASSES entries. */
+#define LDMB_PROFILE_CLASSES 6
+int ldmb_profile_begin(ldmb_handle* h);
+int ldmb_profile_end(ldmb_handle* h, double* ms, double* work, int64_t* launches);
+
 /* ---------------------------------------------------------------- UNet (unet.py) */
 int ldmb_unet_configure(ldmb_handle* h, const ldmb_unet_config* cfg);
 /* One state_dict entry, named as in UNet.state_dict() (no "model." prefix), device fp32,

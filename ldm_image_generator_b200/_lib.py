@@ -47,6 +47,8 @@ SIGNATURES = {
     "ldmb_set_force_simt": (C.c_int, [_H, C.c_int]),
     "ldmb_launch_count": (C.c_int64, [_H]),
     "ldmb_check_device_fault": (C.c_int, [_H, _P]),
+    "ldmb_profile_begin": (C.c_int, [_H]),
+    "ldmb_profile_end": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64P]),
     "ldmb_unet_configure": (C.c_int, [_H, C.POINTER(UNetConfig)]),
     "ldmb_unet_load_param": (C.c_int, [_H, C.c_char_p, _P, _I64P, C.c_int, _P]),
     "ldmb_unet_params_missing": (C.c_int, [_H]),

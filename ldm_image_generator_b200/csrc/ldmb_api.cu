@@ -105,7 +105,18 @@ struct VaeState {
 
 }  // namespace
 
+enum { PK_GEMM_TC = 0, PK_CONV_TC = 1, PK_GEMM_SIMT = 2, PK_NORM = 3, PK_ATTN = 4, PK_OTHER = 5, PK_COUNT = 6 };
+struct ProfRec { int kind; double work; cudaEvent_t a, b; };
+
 struct ldmb_handle {
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  cudaEvent_t get_event() {
+    if (ev_next == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_next++];
+  }
   int device = 0;
   int precision = LDMB_BF16;
   bool force_simt = false;
@@ -135,11 +146,17 @@ int fail(ldmb_handle* h, int code, const char* fmt, ...) {
       return fail(h, LDMB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-#define CKL(call)                                                                                  \
+// A kernel launch on stream `st`: counted, and bracketed by events when profiling is on.
+#define CKLP(KIND_, WORK_, call)                                                                     \
   do {                                                                                             \
+    ProfRec pr__;                                                                                  \
+    const bool p__ = h->prof_on;                                                                   \
+    if (p__) { pr__.kind = (KIND_); pr__.work = (double)(WORK_); pr__.a = h->get_event(); pr__.b = h->get_event(); cudaEventRecord(pr__.a, st); } \
     CK(call);                                                                                      \
     h->launches++;                                                                                 \
+    if (p__) { cudaEventRecord(pr__.b, st); h->prof.push_back(pr__); }                             \
   } while (0)
+#define CKL(call) CKLP(PK_OTHER, 0, call)
 
 int ensure(ldmb_handle* h, DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return LDMB_OK;
@@ -154,9 +171,11 @@ void release(DevBuf& b) {
   b.p = nullptr; b.bytes = 0;
 }
 
-int gemm(ldmb_handle* h, const GemmDesc& d, cudaStream_t s, bool force_simt = false) {
-  if (h->bf16() && !h->force_simt && !force_simt && tc_supported(d)) CKL(launch_gemm_tc(h->tc, d, s));
-  else CKL(launch_gemm_simt(d, h->bf16(), s));
+int gemm(ldmb_handle* h, const GemmDesc& d, cudaStream_t st, bool force_simt = false) {
+  const double flops = 2.0 * d.M * (double)d.N * d.K * (d.batch > 0 ? d.batch : 1);
+  if (h->bf16() && !h->force_simt && !force_simt && tc_supported(d))
+    CKLP(d.amode == AM_CONV3 ? PK_CONV_TC : PK_GEMM_TC, flops, launch_gemm_tc(h->tc, d, st));
+  else CKLP(PK_GEMM_SIMT, flops, launch_gemm_simt(d, h->bf16(), st));
   return LDMB_OK;
 }
 
@@ -240,6 +259,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
   }
   for (auto& v : h->vae) { v.arena.release(); for (auto& b : v.act) release(b); for (auto& b : v.rgb) release(b); }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   tc_context_destroy(h->tc);
   delete h;
 }
@@ -248,6 +268,28 @@ extern "C" const char* ldmb_last_error(const ldmb_handle* h) { return h ? h->err
 extern "C" int ldmb_precision_of(const ldmb_handle* h) { return h ? h->precision : -1; }
 extern "C" int ldmb_set_force_simt(ldmb_handle* h, int on) { if (!h) return LDMB_ERR_INVALID; h->force_simt = on != 0; return LDMB_OK; }
 extern "C" int64_t ldmb_launch_count(const ldmb_handle* h) { return h ? h->launches : 0; }
+extern "C" int ldmb_profile_begin(ldmb_handle* h) {
+  if (!h) return LDMB_ERR_INVALID;
+  h->prof.clear();
+  h->ev_next = 0;
+  h->prof_on = true;
+  return LDMB_OK;
+}
+extern "C" int ldmb_profile_end(ldmb_handle* h, double* ms, double* work, int64_t* launches) {
+  if (!h || !ms || !work || !launches) return LDMB_ERR_INVALID;
+  h->prof_on = false;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0; work[k] = 0; launches[k] = 0; }
+  for (const ProfRec& r : h->prof) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.kind] += t; work[r.kind] += r.work; launches[r.kind] += 1;
+  }
+  h->prof.clear();
+  h->ev_next = 0;
+  return LDMB_OK;
+}
 extern "C" int ldmb_check_device_fault(ldmb_handle* h, void* stream) {
   if (!h) return -1;
   return tc_read_fault(h->tc, static_cast<cudaStream_t>(stream));
@@ -543,7 +585,8 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
   const float* film = static_cast<const float*>(L.film.p) + (size_t)w.lb * n_t * HW * 2 * C;
   int rc;
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
-  CKL(launch_norm_film(x, film, static_cast<const int*>(u.tindex.p), u.xm.p, h->bf16(), M, C, HW, kNormEps, st));
+  CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
+       launch_norm_film(x, film, static_cast<const int*>(u.tindex.p), u.xm.p, h->bf16(), M, C, HW, kNormEps, st));
   // grouped 3x3 (unet.py:30): x += conv(xm); one GEMM per group of 32 channels
   {
     GemmDesc d = gd();
@@ -559,8 +602,9 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE;
     if ((rc = gemm(h, d, st))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
-    CKL(launch_window_attention(u.hbuf.p, u.xm.p, w.b_in, u.att.p, h->bf16(), B, Hl, Wl, C, kHeadDim,
-                                global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, st));
+    CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
+         launch_window_attention(u.hbuf.p, u.xm.p, w.b_in, u.att.p, h->bf16(), B, Hl, Wl, C, kHeadDim,
+                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, st));
     GemmDesc o = gd();
     o.A = u.att.p; o.lda = C; o.W = w.w_out; o.ldw = C; o.bias = w.b_out; o.out = x; o.ldo = C;
     o.M = M; o.N = C; o.K = C; o.epi = EPI_ACCUM_F32;
@@ -986,6 +1030,7 @@ extern "C" int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float
                                      void* stream) {
   if (!h || !x || !film || !out) return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
-  CKL(launch_norm_film(x, film, nullptr, out, h->bf16(), M, C, HW, kNormEps, static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKLP(PK_NORM, (double)M * C * (4 + h->tsize()), launch_norm_film(x, film, nullptr, out, h->bf16(), M, C, HW, kNormEps, st));
   return LDMB_OK;
 }

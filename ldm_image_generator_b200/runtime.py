@@ -91,6 +91,18 @@ class Handle:
     def device_fault(self) -> int:
         return int(self.lib.ldmb_check_device_fault(self.h, stream_ptr(self.device)))
 
+    PROFILE_CLASSES = ("gemm_tcgen05", "conv3x3_tcgen05", "gemm_cuda_core", "channelnorm_film", "window_attention", "other")
+
+    def profile_begin(self) -> None:
+        self.check(self.lib.ldmb_profile_begin(self.h))
+
+    def profile_end(self):
+        """{class: (ms, work, launches)}; work = FLOPs for GEMM/conv classes, bytes for HBM-bound ones."""
+        n = len(self.PROFILE_CLASSES)
+        ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        self.check(self.lib.ldmb_profile_end(self.h, ms, work, cnt))
+        return {k: (ms[i], work[i], int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def sync_params(self, loader, items: Iterable[Tuple[str, torch.Tensor]]) -> int:
         """Upload every state_dict entry whose storage or version changed since the last call."""
         n = 0
