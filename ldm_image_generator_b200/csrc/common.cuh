@@ -25,13 +25,13 @@ struct GemmDesc {
   const void* W; long long ldw;        // weights [rows, K], row stride in elements
   const float* bias;                   // indexed like the weight rows
   void* out; long long ldo;
-  const void* res; long long ldr;      // optional residual in T, added after the activation (EPI_STORE)
+  const void* res; long long ldr;      // optional extra addend in T (EPI_STORE: after the activation; EPI_ACCUM_F32: another branch)
   int M, N, K;                         // N counts accumulator columns
   int epi, act; float slope;
   // expert selection (RandomMoE, modules.py:34-36): which rows of the stacked expert weights a slot uses
   int sel;                             // 0 none; 1 slot = n / sel_span (a|b GEMM); 2 slot = k / sel_span (c GEMM)
   int sel_span;
-  int sel_rows[3];                     // first weight row (and bias index) of slot 0..2
+  int sel_rows[4];                     // first weight row (and bias index) of slot 0..3
   int glu_chunk;                       // EPI_REGLU: a and b columns interleaved in chunks of this many columns
   // grid.z batching (grouped convolution groups, per-block FiLM projections)
   int batch; long long a_koff_b, w_row_b, out_off_b, bias_off_b;

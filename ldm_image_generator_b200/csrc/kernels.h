@@ -36,10 +36,10 @@ cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cu
 // x[b,h,w,:] += ylow[b,h/2,w/2,:]   (nearest Upsample(2) commuted behind the 1x1 conv + skip add, unet.py:85,100-101)
 cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st);
 // Window attention core (attention.py:13-85 + torch MHA): qkv(T) [M,3C] (+ in_proj bias for pad tokens),
-// key bias from xm(T) channel 0 when shift != 0, writes att(T) [M,C]
-cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, bool is_bf16,
-                                    int B, int H, int W, int C, int head_dim, int win_h, int win_w, int shift,
-                                    cudaStream_t st);
+// key bias from xm(T) channel 0 when shift != 0, writes att(T) rows of stride ldo
+cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
+                                    bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
+                                    int shift, cudaStream_t st);
 // decoder_last ConvTranspose (unet.py:78,102) fused with the DDIM update (ddpm.py:81-91).
 // x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; xin/out/noise NCHW fp32 [B,Cin,H*s,W*s]; mode 0 = eps only.
 struct DdimScalars { float c_eps_in, c_div, c_x0, c_eps_out, sigma; int final_step; int enabled; };

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmDesc d) {
         float v = acc[0][i][jj] + bias_of_col(d, z, j);
         if (d.epi == EPI_ACCUM_F32) {
           float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + j;
+          if (d.res) v += to_f(reinterpret_cast<const T*>(d.res)[(long long)m * d.ldr + j]);
           *o += v;
         } else if (d.epi == EPI_STORE_F32) {
           reinterpret_cast<float*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = apply_act(v, d.act, d.slope);
@@ -283,36 +284,51 @@ __global__ void upsample_add_kernel(float* __restrict__ x, const float* __restri
 // Key bias: shift==0 -> pad keys masked (-inf); shift!=0 -> + xm[channel 0] at ((p_i-s) mod Hp, (p_j-s) mod Wp)
 // (attention.py:40 rolls the activation into `mask`), 0 where that position is padding.
 // =====================================================================================
-template <typename T, int D>
-__global__ void __launch_bounds__(64) window_attention_kernel(const T* __restrict__ qkv, const T* __restrict__ xm,
-                                                             const float* __restrict__ b_in, T* __restrict__ att,
-                                                             int H, int W, int C, int wh, int ww, int shift,
-                                                             int Hp, int Wp) {
-  __shared__ float Ks[64][D + 1];
-  __shared__ float Vs[64][D + 1];
+template <typename T> struct Vec16;   // 16-byte vector of T
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* out) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* out) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      out[2 * i] = __low2float(h2); out[2 * i + 1] = __high2float(h2);
+    }
+  }
+};
+
+// One CTA per (image, window, chunk of HC heads); thread (token, head).  K and V of the window are staged in
+// shared memory with 16-byte loads; each thread keeps its query row and output row (D = 32) in registers.
+template <typename T, int D, int HC>
+__global__ void __launch_bounds__(64 * HC) window_attention_kernel(const T* __restrict__ qkv, const T* __restrict__ xm,
+                                                                 const float* __restrict__ b_in, T* __restrict__ att,
+                                                                 long long ldo, int H, int W, int C, int wh, int ww,
+                                                                 int shift, int Hp, int Wp) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int ROW = HC * D;                     // channels of this head chunk
+  __shared__ __align__(16) T Ks[64 * ROW];
+  __shared__ __align__(16) T Vs[64 * ROW];
   __shared__ float kb[64];
+  __shared__ long long rowm[64];
   const int L = wh * ww;
   const int nww = Wp / ww, nwin = (Hp / wh) * nww;
   const int b = blockIdx.x / nwin, win = blockIdx.x % nwin;
   const int wi = win / nww, wj = win % nww;
-  const int head = blockIdx.y;
-  const int tid = threadIdx.x;
-  long long m = -1;
-  bool active = tid < L;
-  if (active) {
+  const int ch0 = blockIdx.y * ROW;               // first channel of the chunk
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  if (tid < L) {
     const int si = tid / ww, sj = tid % ww;
     const int pi = (wi * wh + si - shift + Hp) % Hp, pj = (wj * ww + sj - shift + Wp) % Wp;
     const bool pad = pi >= H || pj >= W;
-    if (!pad) m = ((long long)b * H + pi) * W + pj;
-    const int off = head * D;
-    if (pad) {
-#pragma unroll
-      for (int dd = 0; dd < D; ++dd) { Ks[tid][dd] = b_in[C + off + dd]; Vs[tid][dd] = b_in[2 * C + off + dd]; }
-    } else {
-      const T* row = qkv + m * 3 * C;
-#pragma unroll
-      for (int dd = 0; dd < D; ++dd) { Ks[tid][dd] = to_f(row[C + off + dd]); Vs[tid][dd] = to_f(row[2 * C + off + dd]); }
-    }
+    rowm[tid] = pad ? -1 : ((long long)b * H + pi) * W + pj;
     float bias = 0.f;
     if (shift == 0) {
       bias = pad ? -INFINITY : 0.f;
@@ -323,33 +339,65 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const T* __restric
     kb[tid] = bias;
   }
   __syncthreads();
-  if (!active || m < 0) return;   // outputs at pad positions are cropped (attention.py:56)
+  for (int idx = tid; idx < L * (ROW / VN); idx += nthreads) {
+    const int tok = idx / (ROW / VN), c = (idx % (ROW / VN)) * VN;
+    const long long m = rowm[tok];
+    T* kd = Ks + tok * ROW + c;
+    T* vd = Vs + tok * ROW + c;
+    if (m >= 0) {
+      const T* row = qkv + m * 3 * C + ch0 + c;
+      *reinterpret_cast<uint4*>(kd) = *reinterpret_cast<const uint4*>(row + C);
+      *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(row + 2 * C);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { kd[i] = from_f<T>(b_in[C + ch0 + c + i]); vd[i] = from_f<T>(b_in[2 * C + ch0 + c + i]); }
+    }
+  }
+  __syncthreads();
+  const int tok = tid % L, hl = tid / L;
+  if (hl >= HC) return;
+  const long long m = rowm[tok];
+  if (m < 0) return;                               // outputs at pad positions are cropped (attention.py:56)
   float q[D], acc[D];
   const float scale = (float)sqrt(1.0 / (double)D);
   {
-    const T* row = qkv + m * 3 * C + head * D;
+    const T* row = qkv + m * 3 * C + ch0 + hl * D;
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) { q[dd] = to_f(row[dd]) * scale; acc[dd] = 0.f; }
+    for (int c = 0; c < D; c += VN) Vec16<T>::load(row + c, q + c);
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) { q[dd] *= scale; acc[dd] = 0.f; }
   }
   float mx = -INFINITY, den = 0.f;
   for (int j = 0; j < L; ++j) {
     const float bj = kb[j];
     if (bj == -INFINITY) continue;
+    const T* kr = Ks + j * ROW + hl * D;
     float s = 0.f;
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) s = fmaf(q[dd], Ks[j][dd], s);
+    for (int c = 0; c < D; c += VN) {
+      float kv[VN];
+      Vec16<T>::load(kr + c, kv);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) s = fmaf(q[c + i], kv[i], s);
+    }
     s += bj;
     const float nm = fmaxf(mx, s);
     const float corr = expf(mx - nm), p = expf(s - nm);
     den = den * corr + p;
+    const T* vr = Vs + j * ROW + hl * D;
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) acc[dd] = acc[dd] * corr + p * Vs[j][dd];
+    for (int c = 0; c < D; c += VN) {
+      float vv[VN];
+      Vec16<T>::load(vr + c, vv);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[c + i] = acc[c + i] * corr + p * vv[i];
+    }
     mx = nm;
   }
-  T* o = att + m * C + head * D;
+  T* o = att + m * ldo + ch0 + hl * D;
   const float inv = 1.f / den;
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) o[dd] = from_f<T>(acc[dd] * inv);
+  for (int c = 0; c < D; c += 4) Pack4<T>::store(o + c, acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
 }
 
 // =====================================================================================
@@ -573,20 +621,31 @@ cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W
   return cudaGetLastError();
 }
 
-cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, bool is_bf16,
-                                    int B, int H, int W, int C, int head_dim, int win_h, int win_w, int shift,
-                                    cudaStream_t st) {
-  if (head_dim != 32 || win_h * win_w > 64) return cudaErrorNotSupported;
+template <typename T, int HC>
+static cudaError_t window_attention_launch(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
+                                           int B, int H, int W, int C, int win_h, int win_w, int shift, cudaStream_t st) {
   const int Hp = (H + win_h - 1) / win_h * win_h, Wp = (W + win_w - 1) / win_w * win_w;
-  dim3 grid(B * (Hp / win_h) * (Wp / win_w), C / head_dim);
+  const int L = win_h * win_w, heads = C / 32;
+  dim3 grid(B * (Hp / win_h) * (Wp / win_w), heads / HC);
   if (grid.y > 65535u) return cudaErrorNotSupported;
-  if (is_bf16)
-    window_attention_kernel<bf16, 32><<<grid, 64, 0, st>>>((const bf16*)qkv, (const bf16*)xm, b_in, (bf16*)att, H, W, C,
-                                                          win_h, win_w, shift, Hp, Wp);
-  else
-    window_attention_kernel<float, 32><<<grid, 64, 0, st>>>((const float*)qkv, (const float*)xm, b_in, (float*)att, H, W,
-                                                           C, win_h, win_w, shift, Hp, Wp);
+  int threads = ((L * HC + 31) / 32) * 32;
+  window_attention_kernel<T, 32, HC><<<grid, threads, 0, st>>>((const T*)qkv, (const T*)xm, b_in, (T*)att, ldo, H, W, C,
+                                                              win_h, win_w, shift, Hp, Wp);
   return cudaGetLastError();
+}
+
+cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
+                                    bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
+                                    int shift, cudaStream_t st) {
+  if (head_dim != 32 || win_h * win_w > 64 || C % 32) return cudaErrorNotSupported;
+  const int heads = C / 32;
+  if (is_bf16) {
+    if (heads % 4 == 0) return window_attention_launch<bf16, 4>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+    if (heads % 2 == 0) return window_attention_launch<bf16, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+    return window_attention_launch<bf16, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+  }
+  if (heads % 2 == 0) return window_attention_launch<float, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+  return window_attention_launch<float, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
 }
 
 cudaError_t launch_final(const float* x, const float* w, const float* bias, const float* xin, const float* noise,

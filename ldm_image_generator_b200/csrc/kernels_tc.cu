@@ -224,6 +224,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool full_chunk = n + 32 <= d.N;
         if (d.epi == EPI_ACCUM_F32) {
           float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
+          if (d.res != nullptr) {     // another branch of the block, kept in bf16 (grouped-conv output)
+            const bf16* rp = reinterpret_cast<const bf16*>(d.res) + (long long)m * d.ldr + n;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
+                  v[8 * i + 2 * k] += __low2float(h2);
+                  v[8 * i + 2 * k + 1] += __high2float(h2);
+                }
+              }
+            } else {
+              for (int i = 0; i < 32; ++i) if (n + i < d.N) v[i] += __bfloat162float(rp[i]);
+            }
+          }
           if (full_chunk) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -42,6 +42,8 @@ struct Arena {
     if (base) { cudaFree(base); base = nullptr; }
     cudaError_t e = cudaMalloc(&base, total ? total : 256);
     if (e != cudaSuccess) return e;
+    e = cudaMemset(base, 0, total ? total : 256);   // block-diagonal packings rely on zero fill
+    if (e != cudaSuccess) return e;
     for (auto& s : slots) *s.dst = static_cast<char*>(base) + s.off;
     return cudaSuccess;
   }
@@ -54,8 +56,11 @@ struct Arena {
 struct BlockW {
   int level = 0, C = 0, lb = 0, shift = 0;
   bool attn = false;
-  void *w_ab = nullptr, *w_c = nullptr, *w_g = nullptr, *w_in = nullptr, *w_out = nullptr;
-  float *b_ab = nullptr, *b_c = nullptr, *b_g = nullptr, *b_in = nullptr, *b_out = nullptr;
+  // w_c: [5C, C] stacked c-projections (general, experts 0..3) + for attention blocks the MHA out_proj as rows 5C..6C,
+  //      so that ffn-c and out_proj run as ONE K-concatenated GEMM with a single residual update
+  // w_g: grouped 3x3 conv; C % 64 == 0: block-diagonal pairs of groups [C/64][64][9*64], else per group [C][9*32]
+  void *w_ab = nullptr, *w_c = nullptr, *w_g = nullptr, *w_in = nullptr;
+  float *b_ab = nullptr, *b_c = nullptr, *b_g = nullptr, *b_in = nullptr;
 };
 
 struct LevelW {
@@ -77,7 +82,7 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, att, pooled, ylow, tindex;
+  DevBuf xm, hbuf, qkv, gc, pooled, ylow, tindex;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -253,7 +258,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.att); release(u.pooled); release(u.ylow); release(u.tindex);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.gc); release(u.pooled); release(u.ylow); release(u.tindex);
   if (u.staging) {
     cudaFreeHost(u.staging);
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
@@ -367,8 +372,9 @@ extern "C" int ldmb_unet_configure(ldmb_handle* h, const ldmb_unet_config* cfg) 
     BlockW& w = u.blocks[kv.second];
     const size_t C = w.C;
     a.add(&w.w_ab, 5 * 2 * C * C * ts); a.add((void**)&w.b_ab, 5 * 2 * C * 4);
-    a.add(&w.w_c, 5 * C * C * ts);      a.add((void**)&w.b_c, 5 * C * 4);
-    a.add(&w.w_g, C * 288 * ts);        a.add((void**)&w.b_g, C * 4);
+    const size_t nc = w.attn ? 6 : 5;
+    a.add(&w.w_c, nc * C * C * ts);     a.add((void**)&w.b_c, nc * C * 4);
+    a.add(&w.w_g, C * (C % 64 == 0 ? 576 : 288) * ts); a.add((void**)&w.b_g, C * 4);
     int si, bi; char ed;
     sscanf(kv.first.c_str(), "%c.%d.%d", &ed, &si, &bi);
     char pre[96];
@@ -386,7 +392,6 @@ extern "C" int ldmb_unet_configure(ldmb_handle* h, const ldmb_unet_config* cfg) 
     }
     if (w.attn) {
       a.add(&w.w_in, 3 * C * C * ts); a.add((void**)&w.b_in, 3 * C * 4);
-      a.add(&w.w_out, C * C * ts);    a.add((void**)&w.b_out, C * 4);
       for (const char* n : {"in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"})
         need(std::string("self_attention.attention.") + n);
     }
@@ -482,9 +487,18 @@ extern "C" int ldmb_unet_load_param(ldmb_handle* h, const char* name, const floa
     if (rc) return rc;
     return done();
   }
-  if (rest == "conv.weight") {   // [C, 32, 3, 3] -> [C][tap*32 + ci]
+  if (rest == "conv.weight") {   // [C, 32, 3, 3]
     if (!shape_is(shape, ndim, {C, kHeadDim, 3, 3})) return bad_shape();
-    if ((rc = repack(h, src, w.w_g, true, C, kHeadDim, 9, 288, 9, 1, 288, 1, kHeadDim, st))) return rc;
+    if (C % 64 == 0) {
+      // pairs of groups as one dense 64->64 convolution with block-diagonal weights (zeros from the arena fill):
+      // row (pair p, gl*32+col) holds, per tap, the 32 inputs of group 2p+gl at columns tap*64 + gl*32 + ci
+      for (int gl = 0; gl < 2; ++gl) {
+        const int dims[4] = {C / 64, kHeadDim, kHeadDim, 9};
+        const long long ss[4] = {64 * 288, 288, 9, 1}, ds[4] = {64 * 576, 576, 1, 64};
+        CKL(launch_repack(src + (long long)gl * kHeadDim * 288, toff(h, w.w_g, (long long)gl * (kHeadDim * 576 + kHeadDim)),
+                          h->bf16(), dims, ss, ds, st));
+      }
+    } else if ((rc = repack(h, src, w.w_g, true, C, kHeadDim, 9, 288, 9, 1, 288, 1, kHeadDim, st))) return rc;   // [C][tap*32 + ci]
     return done();
   }
   if (rest == "conv.bias") { if (!shape_is(shape, ndim, {C})) return bad_shape(); if ((rc = copy_f(h, src, w.b_g, C, st))) return rc; return done(); }
@@ -496,8 +510,8 @@ extern "C" int ldmb_unet_load_param(ldmb_handle* h, const char* name, const floa
     const std::string t = rest.substr(strlen("self_attention.attention."));
     if (t == "in_proj_weight") { if (!shape_is(shape, ndim, {3 * C, C})) return bad_shape(); if ((rc = copy_t(h, src, w.w_in, 3LL * C * C, st))) return rc; return done(); }
     if (t == "in_proj_bias") { if (!shape_is(shape, ndim, {3 * C})) return bad_shape(); if ((rc = copy_f(h, src, w.b_in, 3 * C, st))) return rc; return done(); }
-    if (t == "out_proj.weight") { if (!shape_is(shape, ndim, {C, C})) return bad_shape(); if ((rc = copy_t(h, src, w.w_out, (long long)C * C, st))) return rc; return done(); }
-    if (t == "out_proj.bias") { if (!shape_is(shape, ndim, {C})) return bad_shape(); if ((rc = copy_f(h, src, w.b_out, C, st))) return rc; return done(); }
+    if (t == "out_proj.weight") { if (!shape_is(shape, ndim, {C, C})) return bad_shape(); if ((rc = copy_t(h, src, toff(h, w.w_c, 5LL * C * C), (long long)C * C, st))) return rc; return done(); }
+    if (t == "out_proj.bias") { if (!shape_is(shape, ndim, {C})) return bad_shape(); if ((rc = copy_f(h, src, w.b_c + 5LL * C, C, st))) return rc; return done(); }
   }
   return fail(h, LDMB_ERR_INVALID, "unexpected key %s", name);
 }
@@ -529,8 +543,9 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
     }
   }
   if ((rc = ensure(h, u.xm, mx_mc * ts))) return rc;
-  if ((rc = ensure(h, u.hbuf, mx_mc * 3 * ts))) return rc;
-  if ((rc = ensure(h, u.att, mx_mc * ts))) return rc;
+  if ((rc = ensure(h, u.hbuf, mx_mc * 4 * ts))) return rc;
+  if ((rc = ensure(h, u.qkv, mx_mc * 3 * ts))) return rc;
+  if ((rc = ensure(h, u.gc, mx_mc * ts))) return rc;
   if ((rc = ensure(h, u.pooled, (mx_low ? mx_low : 64) * ts))) return rc;
   if ((rc = ensure(h, u.ylow, (mx_low ? mx_low : 64) * 4))) return rc;
   if ((rc = ensure(h, u.tindex, (size_t)B * 4))) return rc;
@@ -587,40 +602,39 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, static_cast<const int*>(u.tindex.p), u.xm.p, h->bf16(), M, C, HW, kNormEps, st));
-  // grouped 3x3 (unet.py:30): x += conv(xm); one GEMM per group of 32 channels
+  // grouped 3x3 (unet.py:30) -> gc (T), added to the residual by the last GEMM's epilogue
   {
     GemmDesc d = gd();
-    d.A = u.xm.p; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = kHeadDim;
-    d.W = w.w_g; d.ldw = 288; d.bias = w.b_g; d.out = x; d.ldo = C;
-    d.M = M; d.N = kHeadDim; d.K = 288; d.epi = EPI_ACCUM_F32;
-    d.batch = C / kHeadDim; d.a_koff_b = kHeadDim; d.w_row_b = kHeadDim; d.out_off_b = kHeadDim; d.bias_off_b = kHeadDim;
+    const int gw = (C % 64 == 0) ? 64 : kHeadDim;          // channels per launch-batch: a pair of groups, or one group
+    d.A = u.xm.p; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = gw;
+    d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = u.gc.p; d.ldo = C;
+    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_STORE;
+    d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
     if ((rc = gemm(h, d, st))) return rc;
   }
-  if (w.attn) {   // WindowAttention (attention.py:13-85)
+  const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
+  if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
-    d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.hbuf.p; d.ldo = 3 * C;
+    d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE;
     if ((rc = gemm(h, d, st))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
     CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
-         launch_window_attention(u.hbuf.p, u.xm.p, w.b_in, u.att.p, h->bf16(), B, Hl, Wl, C, kHeadDim,
+         launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
                                  global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, st));
-    GemmDesc o = gd();
-    o.A = u.att.p; o.lda = C; o.W = w.w_out; o.ldw = C; o.bias = w.b_out; o.out = x; o.ldo = C;
-    o.M = M; o.N = C; o.K = C; o.epi = EPI_ACCUM_F32;
-    if ((rc = gemm(h, o, st))) return rc;
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2
   {
     GemmDesc d = gd();
-    d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = 3 * C;
+    d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_rows[0] = 0; d.sel_rows[1] = (1 + e1) * 2 * C; d.sel_rows[2] = (1 + e2) * 2 * C;
     if ((rc = gemm(h, d, st))) return rc;
+    // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases + gc      (unet.py:44,47: one residual update)
     GemmDesc c = gd();
-    c.A = u.hbuf.p; c.lda = 3 * C; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
-    c.M = M; c.N = C; c.K = 3 * C; c.epi = EPI_ACCUM_F32;
-    c.sel = 2; c.sel_span = C; c.sel_rows[0] = 0; c.sel_rows[1] = (1 + e1) * C; c.sel_rows[2] = (1 + e2) * C;
+    c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
+    c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32; c.res = u.gc.p; c.ldr = C;
+    c.sel = 2; c.sel_span = C; c.sel_rows[0] = 0; c.sel_rows[1] = (1 + e1) * C; c.sel_rows[2] = (1 + e2) * C; c.sel_rows[3] = 5 * C;
     if ((rc = gemm(h, c, st))) return rc;
   }
   return LDMB_OK;
