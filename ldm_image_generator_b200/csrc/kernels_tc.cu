@@ -3,7 +3,10 @@
 // One persistent CTA per SM, 6 warps:
 //   warp 0     TMA producer  (one lane): A tile 128x64 + B tile BNx64 per stage, 128B-swizzled, mbarrier tx-count
 //   warp 1     MMA issuer    (one lane): 4 x tcgen05.mma (M128, N=BN, K16) per stage into one of two TMEM accumulators
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / activation / ReGLU gate / residual -> global
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / activation / ReGLU gate -> 128B-swizzled smem slab
+//              (32 rows x 128 B per warp, double buffered) -> TMA store, or TMA fp32 reduce-add into the residual
+//              stream (x += ... without reading x).  A direct register->global path remains for the ConvTranspose
+//              scatter and for epilogues that add a second tensor.
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue), so the epilogue of
 // tile i overlaps the main loop of tile i+1.
 //
@@ -37,16 +40,20 @@ constexpr int kThreads = 192;
 struct TcTiling {
   int m_tiles, n_tiles, num_kb, total;
   int TW, TH, TB;   // AM_CONV3: the 128-pixel tile is TB images x TH rows x TW columns
+  int tma_out;      // epilogue goes through smem + TMA store / reduce
+  int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
 };
 
 template <int BN> struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + 2 * BN * 4;
+  static constexpr int SLAB_BYTES = 32 * 128;               // one warp's 32 rows x 128 B
+  static constexpr int STAGING_BYTES = 4 * 2 * SLAB_BYTES;   // 4 epilogue warps, double buffered
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
 };
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
@@ -70,13 +77,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 template <int BN, int AMODE>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
-               const TcTiling tl, int* fault) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const GemmDesc d, const TcTiling tl, int* fault) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = tiles + STAGES * Cfg::STAGE_BYTES;      // 1024-aligned (every stage is a multiple of 1024 B)
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -93,6 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (tl.tma_out) ptx::prefetch_tensormap(&tmO);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -174,6 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int et = threadIdx.x - 64;
     uint32_t as = 0, aphase = 0;
+    int slab_sel = 0;
     for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
       const int z = t / tiles_per_z, rem = t % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
@@ -186,6 +196,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < d.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (tl.tma_out) {
+        // ---- smem-staged epilogue: each warp owns rows [q*32, q*32+32) of the tile and its own two 4 KB slabs
+        const int orow = m0 + q * 32 + z * tl.out_row_b;
+        const int ocol_z = z * tl.out_col_b;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        if (d.epi == EPI_STORE || d.epi == EPI_REGLU) {
+          const int accw = d.epi == EPI_REGLU ? 128 : 64;        // accumulator columns consumed per 64-column bf16 slab
+#pragma unroll 1
+          for (int a0 = 0; a0 < BN; a0 += accw) {
+            if (n0 + a0 >= d.N) break;
+            uint8_t* slab = staging + (q * 2 + slab_sel) * Cfg::SLAB_BYTES;
+            if (lane == 0) ptx::bulk_wait_read<1>();              // the store that last used this slab has read it
+            __syncwarp();
+            const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32];
+              float v[32];
+              if (d.epi == EPI_REGLU) {
+                uint32_t rb[32];
+                ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
+                ptx::tmem_ld_32x32(t_row + a0 + 64 + half * 32, rb);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  v[i] = (__uint_as_float(r[i]) + sb[a0 + half * 32 + i]) *
+                         fmaxf(__uint_as_float(rb[i]) + sb[a0 + 64 + half * 32 + i], 0.f);
+              } else {
+                ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = apply_act(__uint_as_float(r[i]) + sb[a0 + half * 32 + i], d.act, d.slope);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                ptx::st_shared_v4(srow + (((half * 4 + u) ^ sw) << 4), pack_bf16(v[8 * u], v[8 * u + 1]),
+                                  pack_bf16(v[8 * u + 2], v[8 * u + 3]), pack_bf16(v[8 * u + 4], v[8 * u + 5]),
+                                  pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int ocol = (d.epi == EPI_REGLU ? ((n0 + a0) >> 1) : (n0 + a0)) + ocol_z;
+              ptx::tma_store_2d(&tmO, slab, ocol, orow);
+              ptx::bulk_commit();
+            }
+            slab_sel ^= 1;
+          }
+        } else {   // EPI_STORE_F32 / EPI_ACCUM_F32: 32 fp32 columns per slab
+#pragma unroll 1
+          for (int a0 = 0; a0 < BN; a0 += 32) {
+            if (n0 + a0 >= d.N) break;
+            uint8_t* slab = staging + (q * 2 + slab_sel) * Cfg::SLAB_BYTES;
+            if (lane == 0) ptx::bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_row + a0, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[a0 + i];
+            if (d.epi == EPI_STORE_F32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              ptx::st_shared_v4(srow + ((u ^ sw) << 4), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                                __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (d.epi == EPI_ACCUM_F32) ptx::tma_reduce_add_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
+              else ptx::tma_store_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
+              ptx::bulk_commit();
+            }
+            slab_sel ^= 1;
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n = n0 + c * 32;
@@ -304,6 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (tl.tma_out && lane == 0) ptx::bulk_wait<0>();       // all of this warp's stores have landed
+    __syncwarp();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -410,8 +503,8 @@ int tc_read_fault(TcContext* ctx, cudaStream_t s) {
 }
 
 template <int BN, int AMODE>
-static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDesc& d,
-                                  const TcTiling& tl, cudaStream_t s) {
+static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                  const GemmDesc& d, const TcTiling& tl, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -420,7 +513,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
     attr_set = true;
   }
   const int grid = tl.total < ctx->num_sms ? tl.total : ctx->num_sms;
-  gemm_tc_kernel<BN, AMODE><<<grid, kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, d, tl, ctx->fault_dev);
+  gemm_tc_kernel<BN, AMODE><<<grid, kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmO, d, tl, ctx->fault_dev);
   return cudaGetLastError();
 }
 
@@ -471,12 +564,40 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
-  if (d.amode == AM_ROWS) {
-    if (bn == 256) return launch_tc_inst<256, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
-    if (bn == 128) return launch_tc_inst<128, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
-    return launch_tc_inst<64, AM_ROWS>(ctx, tmA, tmB, d, tl, s);
+  // ---- output tensor map (smem-staged epilogue), when the shape allows it
+  CUtensorMap tmO;
+  memset(&tmO, 0, sizeof(tmO));
+  tl.tma_out = 0; tl.out_col_b = 0; tl.out_row_b = 0;
+  {
+    const bool f32 = d.epi == EPI_STORE_F32 || d.epi == EPI_ACCUM_F32;
+    const bool mode_ok = (d.epi == EPI_STORE || d.epi == EPI_REGLU || f32) && d.res == nullptr;
+    const int esz = f32 ? 4 : 2;
+    const int slab_cols = f32 ? 32 : 64;
+    const int out_n = d.epi == EPI_REGLU ? d.N / 2 : d.N;
+    bool ok = mode_ok && out_n % slab_cols == 0 && (d.ldo * esz) % 16 == 0 && ((uintptr_t)d.out % 16) == 0;
+    long long rows = d.M;
+    if (ok && batch > 1) {
+      if (d.out_off_b + out_n <= d.ldo && d.out_off_b * (batch - 1) + out_n <= d.ldo) tl.out_col_b = (int)d.out_off_b;
+      else if (d.out_off_b % d.ldo == 0 && d.M % BM == 0) { tl.out_row_b = (int)(d.out_off_b / d.ldo); rows = (long long)tl.out_row_b * (batch - 1) + d.M; }
+      else ok = false;
+    }
+    if (ok) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)d.ldo, (cuuint64_t)rows};
+      const cuuint64_t gstr[1] = {(cuuint64_t)d.ldo * esz};
+      const cuuint32_t box[2] = {(cuuint32_t)slab_cols, 32};
+      r = ctx->encode(&tmO, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, gdim, gstr, box,
+                      ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+      tl.tma_out = 1;
+    }
   }
-  if (bn == 256) return launch_tc_inst<256, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
-  if (bn == 128) return launch_tc_inst<128, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
-  return launch_tc_inst<64, AM_CONV3>(ctx, tmA, tmB, d, tl, s);
+  if (d.amode == AM_ROWS) {
+    if (bn == 256) return launch_tc_inst<256, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
+    if (bn == 128) return launch_tc_inst<128, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
+    return launch_tc_inst<64, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
+  }
+  if (bn == 256) return launch_tc_inst<256, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
+  if (bn == 128) return launch_tc_inst<128, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
+  return launch_tc_inst<64, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
 }

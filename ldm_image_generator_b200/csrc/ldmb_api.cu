@@ -82,7 +82,7 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, gc, pooled, ylow, tindex;
+  DevBuf xm, hbuf, qkv, pooled, ylow, tindex;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -258,7 +258,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.gc); release(u.pooled); release(u.ylow); release(u.tindex);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.tindex);
   if (u.staging) {
     cudaFreeHost(u.staging);
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
@@ -545,7 +545,6 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
   if ((rc = ensure(h, u.xm, mx_mc * ts))) return rc;
   if ((rc = ensure(h, u.hbuf, mx_mc * 4 * ts))) return rc;
   if ((rc = ensure(h, u.qkv, mx_mc * 3 * ts))) return rc;
-  if ((rc = ensure(h, u.gc, mx_mc * ts))) return rc;
   if ((rc = ensure(h, u.pooled, (mx_low ? mx_low : 64) * ts))) return rc;
   if ((rc = ensure(h, u.ylow, (mx_low ? mx_low : 64) * 4))) return rc;
   if ((rc = ensure(h, u.tindex, (size_t)B * 4))) return rc;
@@ -602,13 +601,13 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, static_cast<const int*>(u.tindex.p), u.xm.p, h->bf16(), M, C, HW, kNormEps, st));
-  // grouped 3x3 (unet.py:30) -> gc (T), added to the residual by the last GEMM's epilogue
+  // grouped 3x3 (unet.py:30): x += conv(xm) (TMA fp32 reduce-add on the tcgen05 path; x is not read)
   {
     GemmDesc d = gd();
     const int gw = (C % 64 == 0) ? 64 : kHeadDim;          // channels per launch-batch: a pair of groups, or one group
     d.A = u.xm.p; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = gw;
-    d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = u.gc.p; d.ldo = C;
-    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_STORE;
+    d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = x; d.ldo = C;
+    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32;
     d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
     if ((rc = gemm(h, d, st))) return rc;
   }
@@ -630,10 +629,10 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_rows[0] = 0; d.sel_rows[1] = (1 + e1) * 2 * C; d.sel_rows[2] = (1 + e2) * 2 * C;
     if ((rc = gemm(h, d, st))) return rc;
-    // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases + gc      (unet.py:44,47: one residual update)
+    // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases      (unet.py:44,47: ffn and attention in one update)
     GemmDesc c = gd();
     c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
-    c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32; c.res = u.gc.p; c.ldr = C;
+    c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32;
     c.sel = 2; c.sel_span = C; c.sel_rows[0] = 0; c.sel_rows[1] = (1 + e1) * C; c.sel_rows[2] = (1 + e2) * C; c.sel_rows[3] = 5 * C;
     if ((rc = gemm(h, c, st))) return rc;
   }
