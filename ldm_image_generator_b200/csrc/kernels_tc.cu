@@ -3,7 +3,7 @@
 // One persistent CTA per SM, 6 warps:
 //   warp 0     TMA producer  (one lane): A tile 128x64 + B tile BNx64 per stage, 128B-swizzled, mbarrier tx-count
 //   warp 1     MMA issuer    (one lane): 4 x tcgen05.mma (M128, N=BN, K16) per stage into one of two TMEM accumulators
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / activation / ReGLU gate -> 128B-swizzled smem slab
+//   warps 2-9  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / activation / ReGLU gate -> 128B-swizzled smem slab
 //              (32 rows x 128 B per warp, double buffered) -> TMA store, or TMA fp32 reduce-add into the residual
 //              stream (x += ... without reading x).  A direct register->global path remains for the ConvTranspose
 //              scatter and for epilogues that add a second tensor.
@@ -35,7 +35,8 @@ struct TcContext {
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct TcTiling {
   int m_tiles, n_tiles, num_kb, total;
@@ -52,7 +53,7 @@ template <int BN> struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLAB_BYTES = 32 * 128;               // one warp's 32 rows x 128 B
-  static constexpr int STAGING_BYTES = 4 * 2 * SLAB_BYTES;   // 4 epilogue warps, double buffered
+  static constexpr int STAGING_BYTES = kEpiWarps * 2 * SLAB_BYTES;   // per epilogue warp, double buffered
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
 };
 
@@ -96,7 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kEpiWarps); }
     *s_abort = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
@@ -179,9 +180,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrant warp%4)
+    // ===================================================== epilogue (warps 2..9 -> TMEM lane quadrant warp%4,
+    //                                                        column half (warp-2)/4 of the tile)
     const int q = warp & 3;
+    const int ew = warp - 2;                 // 0..7
+    const int chalf = ew >> 2;               // which half of the tile's accumulator columns this warp drains
     const int et = threadIdx.x - 64;
+    // branch-free activation: act(v) = max(v,0) + ns*min(v,0) with ns = 1 (none), 0 (relu), slope (leaky)
+    const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
     for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
@@ -189,8 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
-      for (int c = et; c < BN; c += 128) sb[c] = (n0 + c < d.N) ? bias_of_col(d, z, n0 + c) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = et; c < BN; c += 32 * kEpiWarps) sb[c] = (n0 + c < d.N) ? bias_of_col(d, z, n0 + c) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
       ptx::tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -204,9 +210,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (d.epi == EPI_STORE || d.epi == EPI_REGLU) {
           const int accw = d.epi == EPI_REGLU ? 128 : 64;        // accumulator columns consumed per 64-column bf16 slab
 #pragma unroll 1
-          for (int a0 = 0; a0 < BN; a0 += accw) {
+          for (int a0 = chalf * accw; a0 < BN; a0 += 2 * accw) {      // slabs interleaved between the two column warps
             if (n0 + a0 >= d.N) break;
-            uint8_t* slab = staging + (q * 2 + slab_sel) * Cfg::SLAB_BYTES;
+            uint8_t* slab = staging + (ew * 2 + slab_sel) * Cfg::SLAB_BYTES;
             if (lane == 0) ptx::bulk_wait_read<1>();              // the store that last used this slab has read it
             __syncwarp();
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
@@ -227,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = apply_act(__uint_as_float(r[i]) + sb[a0 + half * 32 + i], d.act, d.slope);
+                for (int i = 0; i < 32; ++i) { const float t = __uint_as_float(r[i]) + sb[a0 + half * 32 + i]; v[i] = fmaxf(t, 0.f) + ns * fminf(t, 0.f); }
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u)
@@ -246,9 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {   // EPI_STORE_F32 / EPI_ACCUM_F32: 32 fp32 columns per slab
 #pragma unroll 1
-          for (int a0 = 0; a0 < BN; a0 += 32) {
+          for (int a0 = chalf * 32; a0 < BN; a0 += 64) {
             if (n0 + a0 >= d.N) break;
-            uint8_t* slab = staging + (q * 2 + slab_sel) * Cfg::SLAB_BYTES;
+            uint8_t* slab = staging + (ew * 2 + slab_sel) * Cfg::SLAB_BYTES;
             if (lane == 0) ptx::bulk_wait_read<1>();
             __syncwarp();
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
@@ -260,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[a0 + i];
             if (d.epi == EPI_STORE_F32) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f) + ns * fminf(v[i], 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -278,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int n = n0 + c * 32;
         if (n >= d.N) break;
         uint32_t r[32];
@@ -346,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if (d.epi == EPI_STORE_F32) {
           float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f) + ns * fminf(v[i], 0.f);
           if (full_chunk) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -356,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {   // EPI_STORE / EPI_CONVT: bf16 out
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], d.act, d.slope);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f) + ns * fminf(v[i], 0.f);
           bf16* o;
           if (d.epi == EPI_CONVT) o = reinterpret_cast<bf16*>(d.out) + convt_offset(d, m, n);
           else o = reinterpret_cast<bf16*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;

@@ -31,6 +31,10 @@ def main():
     for lvl, C in enumerate((128, 256, 512, 1024)):
         M = B * (32 >> lvl) ** 2
         gemms += [("ffn_ab", M, 6 * C, C), ("ffn_c", M, C, 3 * C), ("qkv", M, 3 * C, C), ("c+out", M, C, 4 * C)]
+    only = os.environ.get("ONLY")          # e.g. ONLY=ffn_ab:65536
+    if only:
+        nm, mm = only.split(":")
+        gemms = [g for g in gemms if g[0] == nm and g[1] == int(mm)]
     NB = 4   # rotate over NB buffer sets so consecutive launches do not hit the same L2 lines
     for name, M, N, K in gemms:
         A = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(NB)]
@@ -41,6 +45,8 @@ def main():
         fl = 2.0 * M * N * K
         by = 2.0 * (M * K + N * K + M * N)
         print(f"gemm {name:8s} M={M:6d} N={N:5d} K={K:5d}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s(alg)")
+    if only:
+        return
     convs = [(B, 32, 32, 512, 512), (B, 64, 64, 256, 256), (B, 128, 128, 128, 128), (B, 256, 256, 64, 64)]
     for (b, H, W_, C, N) in convs:
         bb = max(1, min(b, 16))
