@@ -97,7 +97,11 @@ int ldmb_precision_of(const ldmb_handle* h);
 /* Debug switch: route every bf16 GEMM/convolution through the CUDA-core kernels instead of
  * tcgen05 (to bisect a parity failure).  Never set on a measured run. */
 int ldmb_set_force_simt(ldmb_handle* h, int on);
-/* Number of kernels this library has launched on the handle since creation. */
+/* CUDA-graph replay of the UNet step (default on): the launch sequence of a (batch, resolution, n_t) shape is
+ * captured the second time it is seen and replayed afterwards; everything that changes per step lives in a
+ * device-side step buffer.  Off = every kernel launched individually. */
+int ldmb_set_use_graphs(ldmb_handle* h, int on);
+/* Number of kernels this library has launched on the handle since creation (graph replays count their kernels). */
 int64_t ldmb_launch_count(const ldmb_handle* h);
 /* 0, or the watchdog code a tcgen05 pipeline wrote when an mbarrier wait timed out (device read; synchronises). */
 int ldmb_check_device_fault(ldmb_handle* h, void* stream);

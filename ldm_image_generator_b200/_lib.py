@@ -45,6 +45,7 @@ SIGNATURES = {
     "ldmb_last_error": (C.c_char_p, [_H]),
     "ldmb_precision_of": (C.c_int, [_H]),
     "ldmb_set_force_simt": (C.c_int, [_H, C.c_int]),
+    "ldmb_set_use_graphs": (C.c_int, [_H, C.c_int]),
     "ldmb_launch_count": (C.c_int64, [_H]),
     "ldmb_check_device_fault": (C.c_int, [_H, _P]),
     "ldmb_profile_begin": (C.c_int, [_H]),

@@ -32,11 +32,35 @@ struct GemmDesc {
   int sel;                             // 0 none; 1 slot = n / sel_span (a|b GEMM); 2 slot = k / sel_span (c GEMM)
   int sel_span;
   int sel_rows[4];                     // first weight row (and bias index) of slot 0..3
+  // Device-side plan entry {skip, e1, e2, -} of the SwinBlock this launch belongs to (NULL: use sel_rows as given).
+  // Lets one captured CUDA graph serve every step although the Python-RNG decisions differ per step:
+  // slot q > 0 uses rows (1 + e_q) * sel_stride, slot 3 (attention out_proj) rows 5 * sel_stride; skip => kernel exits.
+  const int* plan; int sel_stride;
   int glu_chunk;                       // EPI_REGLU: a and b columns interleaved in chunks of this many columns
   // grid.z batching (grouped convolution groups, per-block FiLM projections)
   int batch; long long a_koff_b, w_row_b, out_off_b, bias_off_b;
   int ctH, ctW, ctC;                   // EPI_CONVT: input height, width, output channels
 };
+
+// Per-call parameters that change every step; kernels read them from device memory so the launch sequence is static.
+struct StepParams {
+  const float* x_in; float* out; const float* noise;
+  float c_eps_in, c_div, c_x0, c_eps_out, sigma;
+  int final_step, ddim_enabled;
+};
+
+// Resolve the device-side plan into sel_rows; returns true when the block is skipped (stochastic depth, unet.py:39-40).
+__device__ __forceinline__ bool resolve_plan(GemmDesc& d) {
+  if (d.plan == nullptr) return false;
+  if (d.plan[0] != 0) return true;
+  if (d.sel != 0) {
+    d.sel_rows[0] = 0;
+    d.sel_rows[1] = (1 + d.plan[1]) * d.sel_stride;
+    d.sel_rows[2] = (1 + d.plan[2]) * d.sel_stride;
+    d.sel_rows[3] = 5 * d.sel_stride;
+  }
+  return false;
+}
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

@@ -21,12 +21,14 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
 
 // ---- UNet pieces
 // encoder_first (unet.py:77,90): x NCHW fp32 [B,Cin,H*s,W*s] -> out fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]
-cudaError_t launch_stem(const float* x, const float* w, const float* bias, float* out,
+// x is read through sp->x_in (device-side step parameters)
+cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias, float* out,
                         int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
 // ChannelNorm + FiLM (modules.py:23-25, unet.py:22): out(T)[m,c] = norm(x[m,:])[c]*film[row,c] + film[row,C+c]
 // film row = t_index[m / HW] * HW + m % HW  (t_index may be NULL -> 0)
+// skip (device, may be NULL): non-zero => the block is skipped this step and the kernel exits
 cudaError_t launch_norm_film(const float* x, const float* film, const int* t_index, void* out, bool is_bf16,
-                             int M, int C, int HW, float eps, cudaStream_t st);
+                             int M, int C, int HW, float eps, const int* skip, cudaStream_t st);
 // emb(T)[ti*HW + p][0:C] = pe[p][:],  [C:2C] = te[ti][:]      (unet.py:19)
 cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool is_bf16, int n_t, int HW, int C,
                              cudaStream_t st);
@@ -39,12 +41,12 @@ cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W
 // key bias from xm(T) channel 0 when shift != 0, writes att(T) rows of stride ldo
 cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
                                     bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
-                                    int shift, cudaStream_t st);
+                                    int shift, const int* skip, cudaStream_t st);
 // decoder_last ConvTranspose (unet.py:78,102) fused with the DDIM update (ddpm.py:81-91).
-// x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; xin/out/noise NCHW fp32 [B,Cin,H*s,W*s]; mode 0 = eps only.
-struct DdimScalars { float c_eps_in, c_div, c_x0, c_eps_out, sigma; int final_step; int enabled; };
-cudaError_t launch_final(const float* x, const float* w, const float* bias, const float* xin, const float* noise,
-                         float* out, DdimScalars co, int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
+// x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; x_in/out/noise NCHW fp32 [B,Cin,H*s,W*s]; ddim_enabled 0 = eps only.
+// sp (device): x_in / out / noise pointers and the DDIM scalars of this step.
+cudaError_t launch_final(const float* x, const float* w, const float* bias, const StepParams* sp,
+                         int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
 
 // ---- VAE pieces
 // 1x1 conv from an NCHW fp32 tensor with few channels (latent 8 / RGB 3) into NHWC T

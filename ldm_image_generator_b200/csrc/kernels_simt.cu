@@ -13,8 +13,10 @@ namespace {
 // toy channel counts that cannot be tiled for tcgen05.
 // =====================================================================================
 template <typename T, int AMODE, bool GLU>
-__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmDesc d) {
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc dparam) {
   constexpr int BM = 64, BN = 64, BK = 16, NW = GLU ? 2 : 1;
+  GemmDesc d = dparam;
+  if (resolve_plan(d)) return;
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[NW][BK][BN + 4];
   const int z = blockIdx.z;
@@ -182,7 +184,8 @@ template <> struct Pack4<bf16> {
 template <typename T, int MAXV>
 __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict__ x, const float* __restrict__ film,
                                                         const int* __restrict__ t_index, T* __restrict__ out,
-                                                        int M, int C, int HW, float eps) {
+                                                        int M, int C, int HW, float eps, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps_per_grid) {
@@ -311,7 +314,8 @@ template <typename T, int D, int HC>
 __global__ void __launch_bounds__(64 * HC) window_attention_kernel(const T* __restrict__ qkv, const T* __restrict__ xm,
                                                                  const float* __restrict__ b_in, T* __restrict__ att,
                                                                  long long ldo, int H, int W, int C, int wh, int ww,
-                                                                 int shift, int Hp, int Wp) {
+                                                                 int shift, int Hp, int Wp, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
   constexpr int VN = Vec16<T>::N;
   constexpr int ROW = HC * D;                     // channels of this head chunk
   __shared__ __align__(16) T Ks[64 * ROW];
@@ -405,9 +409,10 @@ __global__ void __launch_bounds__(64 * HC) window_attention_kernel(const T* __re
 // =====================================================================================
 // in: NCHW fp32 [B, Cin, H*s, W*s], k = stride = s (s = 1: 1x1 conv).  out: [B*H*W, Cout] in TO.
 template <typename TO>
-__global__ void pointwise_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                    const float* __restrict__ bias, TO* __restrict__ out,
+__global__ void pointwise_in_kernel(const float* __restrict__ x, const StepParams* __restrict__ sp,
+                                    const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out,
                                     int B, int Cin, int H, int W, int s, int Cout) {
+  if (sp != nullptr) x = sp->x_in;
   const long long total = (long long)B * H * W * Cout;
   const int J = Cin * s * s;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -459,10 +464,13 @@ __device__ __forceinline__ void reduce_pixels_32(const T* __restrict__ x, long l
 
 // decoder_last (ConvTranspose2d k=s stride=s, unet.py:78,102) + DDIM update (ddpm.py:81-91)
 __global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, const float* __restrict__ xin,
-                                                    const float* __restrict__ noise, float* __restrict__ out,
-                                                    DdimScalars co, int B, int Cin, int H, int W, int s, int C0) {
+                                                    const float* __restrict__ bias, const StepParams* __restrict__ sp,
+                                                    int B, int Cin, int H, int W, int s, int C0) {
   __shared__ float e[32][33];
+  const StepParams co = *sp;
+  const float* __restrict__ xin = co.x_in;
+  const float* __restrict__ noise = co.noise;
+  float* __restrict__ out = co.out;
   const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * 32;
   const int J = Cin * s * s;
   reduce_pixels_32<float>(x, m0, M, C0, J, w, true, e);
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x,
     const long long o = (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
     const float eps = e[j][p] + bias[ci];
     float r = eps;
-    if (co.enabled) {
+    if (co.ddim_enabled) {
       const float x0 = (xin[o] - co.c_eps_in * eps) / co.c_div;
       if (co.final_step) r = x0;
       else {
@@ -551,39 +559,39 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
   return cudaGetLastError();
 }
 
-cudaError_t launch_stem(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
+cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
                         int s, int C0, cudaStream_t st) {
   const long long total = (long long)B * H * W * C0;
-  pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, H, W, s, C0);
+  pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }
 
 cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float* bias, void* out, bool is_bf16,
                                      int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
   const long long total = (long long)B * H * W * Cout;
-  if (is_bf16) pointwise_in_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
-  else pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
+  if (is_bf16) pointwise_in_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(x, nullptr, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
+  else pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, nullptr, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
-                                      int HW, float eps, cudaStream_t st) {
+                                      int HW, float eps, const int* skip, cudaStream_t st) {
   const int blocks = grid_for((long long)M * 32, 256, 148 * 8);
-  if (C <= 128) norm_film_kernel<T, 1><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
-  else if (C <= 256) norm_film_kernel<T, 2><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
-  else if (C <= 512) norm_film_kernel<T, 4><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
-  else if (C <= 1024) norm_film_kernel<T, 8><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
-  else if (C <= 2048) norm_film_kernel<T, 16><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps);
+  if (C <= 128) norm_film_kernel<T, 1><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 256) norm_film_kernel<T, 2><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 512) norm_film_kernel<T, 4><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 1024) norm_film_kernel<T, 8><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 2048) norm_film_kernel<T, 16><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
   else return cudaErrorNotSupported;
   return cudaGetLastError();
 }
 
 cudaError_t launch_norm_film(const float* x, const float* film, const int* t_index, void* out, bool is_bf16, int M,
-                             int C, int HW, float eps, cudaStream_t st) {
+                             int C, int HW, float eps, const int* skip, cudaStream_t st) {
   if (C % 4 != 0) return cudaErrorNotSupported;
-  return is_bf16 ? norm_film_dispatch<bf16>(x, film, t_index, (bf16*)out, M, C, HW, eps, st)
-                 : norm_film_dispatch<float>(x, film, t_index, (float*)out, M, C, HW, eps, st);
+  return is_bf16 ? norm_film_dispatch<bf16>(x, film, t_index, (bf16*)out, M, C, HW, eps, skip, st)
+                 : norm_film_dispatch<float>(x, film, t_index, (float*)out, M, C, HW, eps, skip, st);
 }
 
 cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool is_bf16, int n_t, int HW, int C,
@@ -623,36 +631,37 @@ cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W
 
 template <typename T, int HC>
 static cudaError_t window_attention_launch(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
-                                           int B, int H, int W, int C, int win_h, int win_w, int shift, cudaStream_t st) {
+                                           int B, int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
+                                           cudaStream_t st) {
   const int Hp = (H + win_h - 1) / win_h * win_h, Wp = (W + win_w - 1) / win_w * win_w;
   const int L = win_h * win_w, heads = C / 32;
   dim3 grid(B * (Hp / win_h) * (Wp / win_w), heads / HC);
   if (grid.y > 65535u) return cudaErrorNotSupported;
   int threads = ((L * HC + 31) / 32) * 32;
   window_attention_kernel<T, 32, HC><<<grid, threads, 0, st>>>((const T*)qkv, (const T*)xm, b_in, (T*)att, ldo, H, W, C,
-                                                              win_h, win_w, shift, Hp, Wp);
+                                                              win_h, win_w, shift, Hp, Wp, skip);
   return cudaGetLastError();
 }
 
 cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
                                     bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
-                                    int shift, cudaStream_t st) {
+                                    int shift, const int* skip, cudaStream_t st) {
   if (head_dim != 32 || win_h * win_w > 64 || C % 32) return cudaErrorNotSupported;
   const int heads = C / 32;
   if (is_bf16) {
-    if (heads % 4 == 0) return window_attention_launch<bf16, 4>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
-    if (heads % 2 == 0) return window_attention_launch<bf16, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
-    return window_attention_launch<bf16, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+    if (heads % 4 == 0) return window_attention_launch<bf16, 4>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
+    if (heads % 2 == 0) return window_attention_launch<bf16, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
+    return window_attention_launch<bf16, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
   }
-  if (heads % 2 == 0) return window_attention_launch<float, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
-  return window_attention_launch<float, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, st);
+  if (heads % 2 == 0) return window_attention_launch<float, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
+  return window_attention_launch<float, 1>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
 }
 
-cudaError_t launch_final(const float* x, const float* w, const float* bias, const float* xin, const float* noise,
-                         float* out, DdimScalars co, int B, int Cin, int H, int W, int s, int C0, cudaStream_t st) {
+cudaError_t launch_final(const float* x, const float* w, const float* bias, const StepParams* sp, int B, int Cin, int H,
+                         int W, int s, int C0, cudaStream_t st) {
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
-  final_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(x, w, bias, xin, noise, out, co, B, Cin, H, W, s, C0);
+  final_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(x, w, bias, sp, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }
 

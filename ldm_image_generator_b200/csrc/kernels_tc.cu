@@ -79,8 +79,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int AMODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const GemmDesc d, const TcTiling tl, int* fault) {
+               const __grid_constant__ CUtensorMap tmO, const GemmDesc dparam, const TcTiling tl, int* fault) {
   using Cfg = TcCfg<BN>;
+  GemmDesc d = dparam;
+  if (resolve_plan(d)) return;     // block skipped this step: uniform exit before any barrier / TMEM allocation
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -561,6 +563,8 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
     long long rows = d.N;
     if (d.sel == 1) { rows = 0; for (int q = 0; q < d.N / d.sel_span; ++q) if (d.sel_rows[q] + d.sel_span > rows) rows = d.sel_rows[q] + d.sel_span; }
     if (d.sel == 2) { rows = 0; for (int q = 0; q < d.K / d.sel_span; ++q) if (d.sel_rows[q] + d.N > rows) rows = d.sel_rows[q] + d.N; }
+    if (d.plan != nullptr && d.sel == 1) rows = 5LL * d.sel_stride;      // any expert may be picked at replay time
+    if (d.plan != nullptr && d.sel == 2) rows = (d.K / d.sel_span == 4 ? 6LL : 5LL) * d.sel_stride;
     rows += (long long)(batch - 1) * d.w_row_b;
     const cuuint64_t gdim[2] = {(cuuint64_t)d.ldw, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)d.ldw * 2};

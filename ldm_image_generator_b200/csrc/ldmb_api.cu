@@ -82,7 +82,13 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, pooled, ylow, tindex;
+  DevBuf xm, hbuf, qkv, pooled, ylow, stepbuf;
+  // device views into stepbuf (layout fixed per (B, n_t)): StepParams | plan[n_blocks][4] | t_index[B] | te tables
+  const StepParams* sp_dev = nullptr; const int* plan_dev = nullptr; const int* tindex_dev = nullptr;
+  struct GraphEntry { int B, Hs, Ws, n_t; unsigned long long epoch; cudaGraphExec_t exec; long long launches; int seen; };
+  std::vector<GraphEntry> graphs;
+  unsigned long long ws_epoch = 0;     // bumped whenever a workspace is reallocated (cached graphs hold raw pointers)
+  bool use_graphs = true;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -165,6 +171,7 @@ int fail(ldmb_handle* h, int code, const char* fmt, ...) {
 
 int ensure(ldmb_handle* h, DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return LDMB_OK;
+  h->unet.ws_epoch++;
   if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
   CK(cudaMalloc(&b.p, bytes ? bytes : 256));
   b.bytes = bytes;
@@ -258,7 +265,8 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.tindex);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf);
+  for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.staging) {
     cudaFreeHost(u.staging);
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
@@ -534,7 +542,6 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
     if ((rc = ensure(h, L.emb, (size_t)n_t * HW * 2 * C * ts))) return rc;
     if ((rc = ensure(h, L.h1, (size_t)n_t * HW * L.nb * 4 * C * ts))) return rc;
     if ((rc = ensure(h, L.film, (size_t)L.nb * n_t * HW * 2 * C * 4))) return rc;
-    if ((rc = ensure(h, L.te, (size_t)n_t * C * 4))) return rc;
     if (M * C > mx_mc) mx_mc = M * C;
     if (l < S - 1) {
       const size_t Ml = M / 4, Cn = u.cfg.channels[l + 1];
@@ -547,7 +554,6 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
   if ((rc = ensure(h, u.qkv, mx_mc * 3 * ts))) return rc;
   if ((rc = ensure(h, u.pooled, (mx_low ? mx_low : 64) * ts))) return rc;
   if ((rc = ensure(h, u.ylow, (mx_low ? mx_low : 64) * 4))) return rc;
-  if ((rc = ensure(h, u.tindex, (size_t)B * 4))) return rc;
   return LDMB_OK;
 }
 
@@ -588,26 +594,24 @@ extern "C" int ldmb_unet_set_position_table(ldmb_handle* h, int level, const flo
 
 namespace {
 
-int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, const int32_t* pe, cudaStream_t st) {
-  if (pe[0]) return LDMB_OK;                       // stochastic depth skipped this block (unet.py:39-40)
+int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, int Wl, int n_t, cudaStream_t st) {
   UNetState& u = h->unet;
   LevelW& L = u.levels[w.level];
   const int C = w.C, HW = Hl * Wl, M = B * HW;
-  const int e1 = pe[1], e2 = pe[2];
-  if (e1 < 0 || e1 >= kExperts || e2 < 0 || e2 >= kExperts) return fail(h, LDMB_ERR_INVALID, "plan: expert index out of range");
+  const int* pl = u.plan_dev + 4 * block_index;     // {skip, e1, e2, -}: every kernel of the block reads it on the device
   float* x = static_cast<float*>(L.xs.p);
   const float* film = static_cast<const float*>(L.film.p) + (size_t)w.lb * n_t * HW * 2 * C;
   int rc;
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
-       launch_norm_film(x, film, static_cast<const int*>(u.tindex.p), u.xm.p, h->bf16(), M, C, HW, kNormEps, st));
+       launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, pl, st));
   // grouped 3x3 (unet.py:30): x += conv(xm) (TMA fp32 reduce-add on the tcgen05 path; x is not read)
   {
     GemmDesc d = gd();
     const int gw = (C % 64 == 0) ? 64 : kHeadDim;          // channels per launch-batch: a pair of groups, or one group
     d.A = u.xm.p; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = gw;
     d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = x; d.ldo = C;
-    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32;
+    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32; d.plan = pl;
     d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
     if ((rc = gemm(h, d, st))) return rc;
   }
@@ -615,91 +619,42 @@ int run_block(ldmb_handle* h, const BlockW& w, int B, int Hl, int Wl, int n_t, c
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
-    d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE;
+    d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE; d.plan = pl;
     if ((rc = gemm(h, d, st))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
     CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
          launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
-                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, st));
+                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, pl, st));
   }
-  // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2
+  // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
   {
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
-    d.sel = 1; d.sel_span = 2 * C; d.sel_rows[0] = 0; d.sel_rows[1] = (1 + e1) * 2 * C; d.sel_rows[2] = (1 + e2) * 2 * C;
+    d.sel = 1; d.sel_span = 2 * C; d.sel_stride = 2 * C; d.plan = pl;
     if ((rc = gemm(h, d, st))) return rc;
     // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases      (unet.py:44,47: ffn and attention in one update)
     GemmDesc c = gd();
     c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
     c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32;
-    c.sel = 2; c.sel_span = C; c.sel_rows[0] = 0; c.sel_rows[1] = (1 + e1) * C; c.sel_rows[2] = (1 + e2) * C; c.sel_rows[3] = 5 * C;
+    c.sel = 2; c.sel_span = C; c.sel_stride = C; c.plan = pl;
     if ((rc = gemm(h, c, st))) return rc;
   }
   return LDMB_OK;
 }
 
-}  // namespace
-
-extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
-                                 const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
-                                 const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
-  if (!h || !x_dev || !out_dev || !t_index || !te_host || !plan) return LDMB_ERR_INVALID;
+// Every launch of one UNet step, in order, on `st`.  Static given (B, Hs, Ws, n_t): all per-step values are read from
+// the device-side step buffer, so the sequence can be captured once into a CUDA graph and replayed.
+int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* const* te_dev, cudaStream_t st) {
   UNetState& u = h->unet;
-  if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
-  if (!u.missing.empty())
-    return fail(h, LDMB_ERR_STATE, "%d UNet parameters not loaded (first: %s)", (int)u.missing.size(), u.missing.begin()->c_str());
-  CK(cudaSetDevice(h->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const ldmb_unet_config& cfg = u.cfg;
   const int S = cfg.num_levels, s = cfg.stem_size;
-  if (B < 1 || n_t < 1 || H < s || W < s || H % s || W % s) return fail(h, LDMB_ERR_INVALID, "forward: bad batch/resolution");
-  const int Hs = H / s, Ws = W / s;
-  if ((Hs % (1 << (S - 1))) || (Ws % (1 << (S - 1))))
-    return fail(h, LDMB_ERR_INVALID, "resolution %dx%d is not divisible by 2^%d: skip shapes would not match (unet.py:101)", Hs, Ws, S - 1);
-  for (int b = 0; b < B; ++b) if (t_index[b] < 0 || t_index[b] >= n_t) return fail(h, LDMB_ERR_INVALID, "t_index out of range");
-  if (coef && coef->sigma != 0.f && !noise_dev) return fail(h, LDMB_ERR_INVALID, "sigma != 0 needs a noise tensor");
   int rc;
-  if ((rc = unet_reserve(h, B, Hs, Ws, n_t))) return rc;
-  for (int l = 0; l < S; ++l)
-    if (u.levels[l].peH != (Hs >> l) || u.levels[l].peW != (Ws >> l) || !u.levels[l].pe.p)
-      return fail(h, LDMB_ERR_STATE, "position table of level %d not set for %dx%d", l, Hs >> l, Ws >> l);
-
-  // ---- stage the small host tables through a pinned ring (stream-ordered, no device sync)
-  size_t need = (size_t)B * 4;
-  for (int l = 0; l < S; ++l) need += (size_t)n_t * u.levels[l].C * 4;
-  if (need > u.staging_slot_bytes) {
-    CK(cudaDeviceSynchronize());
-    if (u.staging) CK(cudaFreeHost(u.staging));
-    u.staging_slot_bytes = need * 2 + 4096;
-    CK(cudaMallocHost((void**)&u.staging, u.staging_slot_bytes * kStagingSlots));
-    for (int i = 0; i < kStagingSlots; ++i) {
-      if (!u.staging_ev[i]) CK(cudaEventCreateWithFlags(&u.staging_ev[i], cudaEventDisableTiming));
-      u.staging_used[i] = false;
-    }
-  }
-  const int slot = u.staging_next;
-  u.staging_next = (slot + 1) % kStagingSlots;
-  if (u.staging_used[slot]) CK(cudaEventSynchronize(u.staging_ev[slot]));
-  char* sp = u.staging + (size_t)slot * u.staging_slot_bytes;
-  memcpy(sp, t_index, (size_t)B * 4);
-  CK(cudaMemcpyAsync(u.tindex.p, sp, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  size_t off = (size_t)B * 4;
-  for (int l = 0; l < S; ++l) {
-    const size_t n = (size_t)n_t * u.levels[l].C * 4;
-    if (!te_host[l]) return fail(h, LDMB_ERR_INVALID, "te_host[%d] is NULL", l);
-    memcpy(sp + off, te_host[l], n);
-    CK(cudaMemcpyAsync(u.levels[l].te.p, sp + off, n, cudaMemcpyHostToDevice, st));
-    off += n;
-  }
-  CK(cudaEventRecord(u.staging_ev[slot], st));
-  u.staging_used[slot] = true;
-
   // ---- Encodings (unet.py:18-21), hoisted: depends on (t,h,w) only -> once per call for all blocks of a level
   for (int l = 0; l < S; ++l) {
     LevelW& L = u.levels[l];
     const int C = L.C, HW = (Hs >> l) * (Ws >> l), Mt = n_t * HW;
-    CKL(launch_emb_build(static_cast<const float*>(L.pe.p), static_cast<const float*>(L.te.p), L.emb.p, h->bf16(), n_t, HW, C, st));
+    CKL(launch_emb_build(static_cast<const float*>(L.pe.p), te_dev[l], L.emb.p, h->bf16(), n_t, HW, C, st));
     GemmDesc a = gd();
     a.A = L.emb.p; a.lda = 2 * C; a.W = L.w1; a.ldw = 2 * C; a.bias = L.b1; a.out = L.h1.p; a.ldo = (long long)L.nb * 4 * C;
     a.M = Mt; a.N = L.nb * 4 * C; a.K = 2 * C; a.epi = EPI_STORE; a.act = ACT_RELU;
@@ -710,16 +665,15 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
     b.batch = L.nb; b.a_koff_b = 4 * C; b.w_row_b = 2 * C; b.out_off_b = (long long)Mt * 2 * C; b.bias_off_b = 2 * C;
     if ((rc = gemm(h, b, st))) return rc;
   }
-
   // ---- encoder_first (unet.py:90)
-  CKL(launch_stem(x_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
+  CKL(launch_stem(u.sp_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
                   cfg.channels[0], st));
   // ---- encoder (unet.py:92-98)
   int bi = 0;
   for (int l = 0; l < S; ++l) {
     const int Hl = Hs >> l, Wl = Ws >> l;
     for (int b = 0; b < cfg.blocks[l]; ++b, ++bi)
-      if ((rc = run_block(h, u.blocks[bi], B, Hl, Wl, n_t, plan + 3 * bi, st))) return rc;
+      if ((rc = run_block(h, u.blocks[bi], bi, B, Hl, Wl, n_t, st))) return rc;
     if (l < S - 1) {
       // ch_conv = Conv1x1 then AvgPool2 (unet.py:83); the two commute, pool first = 4x fewer FLOPs
       LevelW& L = u.levels[l];
@@ -747,17 +701,138 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
       CKL(launch_upsample_add(static_cast<float*>(L.xs.p), static_cast<const float*>(u.ylow.p), B, Hl, Wl, C, st));
     }
     for (int b = 0; b < cfg.blocks[l]; ++b, ++bi)
-      if ((rc = run_block(h, u.blocks[bi], B, Hl, Wl, n_t, plan + 3 * bi, st))) return rc;
+      if ((rc = run_block(h, u.blocks[bi], bi, B, Hl, Wl, n_t, st))) return rc;
   }
   // ---- decoder_last (unet.py:102) + DDIM update (ddpm.py:81-91)
-  DdimScalars co{};
-  if (coef) {
-    co.c_eps_in = coef->c_eps_in; co.c_div = coef->c_div; co.c_x0 = coef->c_x0; co.c_eps_out = coef->c_eps_out;
-    co.sigma = coef->sigma; co.final_step = coef->final_step; co.enabled = 1;
-  }
-  CKL(launch_final(static_cast<const float*>(u.levels[0].xs.p), u.w_last, u.b_last, x_dev, noise_dev, out_dev, co, B,
-                   cfg.input_channels, Hs, Ws, s, cfg.channels[0], st));
+  CKL(launch_final(static_cast<const float*>(u.levels[0].xs.p), u.w_last, u.b_last, u.sp_dev, B, cfg.input_channels, Hs, Ws, s,
+                   cfg.channels[0], st));
   return LDMB_OK;
+}
+
+}  // namespace
+
+extern "C" int ldmb_set_use_graphs(ldmb_handle* h, int on) {
+  if (!h) return LDMB_ERR_INVALID;
+  h->unet.use_graphs = on != 0;
+  return LDMB_OK;
+}
+
+extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
+                                 const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
+                                 const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
+  if (!h || !x_dev || !out_dev || !t_index || !te_host || !plan) return LDMB_ERR_INVALID;
+  UNetState& u = h->unet;
+  if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
+  if (!u.missing.empty())
+    return fail(h, LDMB_ERR_STATE, "%d UNet parameters not loaded (first: %s)", (int)u.missing.size(), u.missing.begin()->c_str());
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const ldmb_unet_config& cfg = u.cfg;
+  const int S = cfg.num_levels, s = cfg.stem_size;
+  const int nblk = (int)u.blocks.size();
+  if (B < 1 || n_t < 1 || H < s || W < s || H % s || W % s) return fail(h, LDMB_ERR_INVALID, "forward: bad batch/resolution");
+  const int Hs = H / s, Ws = W / s;
+  if ((Hs % (1 << (S - 1))) || (Ws % (1 << (S - 1))))
+    return fail(h, LDMB_ERR_INVALID, "resolution %dx%d is not divisible by 2^%d: skip shapes would not match (unet.py:101)", Hs, Ws, S - 1);
+  for (int b = 0; b < B; ++b) if (t_index[b] < 0 || t_index[b] >= n_t) return fail(h, LDMB_ERR_INVALID, "t_index out of range");
+  for (int b = 0; b < nblk; ++b)
+    if (!plan[3 * b] && (plan[3 * b + 1] < 0 || plan[3 * b + 1] >= kExperts || plan[3 * b + 2] < 0 || plan[3 * b + 2] >= kExperts))
+      return fail(h, LDMB_ERR_INVALID, "plan: expert index out of range");
+  if (coef && coef->sigma != 0.f && !noise_dev) return fail(h, LDMB_ERR_INVALID, "sigma != 0 needs a noise tensor");
+  int rc;
+  if ((rc = unet_reserve(h, B, Hs, Ws, n_t))) return rc;
+  for (int l = 0; l < S; ++l)
+    if (u.levels[l].peH != (Hs >> l) || u.levels[l].peW != (Ws >> l) || !u.levels[l].pe.p)
+      return fail(h, LDMB_ERR_STATE, "position table of level %d not set for %dx%d", l, Hs >> l, Ws >> l);
+
+  // ---- step buffer layout: StepParams | plan[nblk][4] | t_index[B] | te tables (16-byte aligned pieces)
+  auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
+  const size_t off_plan = al(sizeof(StepParams));
+  const size_t off_tidx = off_plan + al((size_t)nblk * 16);
+  size_t off_te[LDMB_MAX_LEVELS];
+  size_t total = off_tidx + al((size_t)B * 4);
+  for (int l = 0; l < S; ++l) { off_te[l] = total; total += al((size_t)n_t * u.levels[l].C * 4); }
+  if ((rc = ensure(h, u.stepbuf, total))) return rc;
+  char* sb = static_cast<char*>(u.stepbuf.p);
+  u.sp_dev = reinterpret_cast<const StepParams*>(sb);
+  u.plan_dev = reinterpret_cast<const int*>(sb + off_plan);
+  u.tindex_dev = reinterpret_cast<const int*>(sb + off_tidx);
+  const float* te_dev[LDMB_MAX_LEVELS];
+  for (int l = 0; l < S; ++l) te_dev[l] = reinterpret_cast<const float*>(sb + off_te[l]);
+
+  // ---- fill one slot of the pinned staging ring and upload it with a single stream-ordered copy
+  if (total > u.staging_slot_bytes) {
+    CK(cudaDeviceSynchronize());
+    if (u.staging) CK(cudaFreeHost(u.staging));
+    u.staging_slot_bytes = total * 2 + 4096;
+    CK(cudaMallocHost((void**)&u.staging, u.staging_slot_bytes * kStagingSlots));
+    for (int i = 0; i < kStagingSlots; ++i) {
+      if (!u.staging_ev[i]) CK(cudaEventCreateWithFlags(&u.staging_ev[i], cudaEventDisableTiming));
+      u.staging_used[i] = false;
+    }
+  }
+  const int slot = u.staging_next;
+  u.staging_next = (slot + 1) % kStagingSlots;
+  if (u.staging_used[slot]) CK(cudaEventSynchronize(u.staging_ev[slot]));
+  char* hp = u.staging + (size_t)slot * u.staging_slot_bytes;
+  StepParams spv;
+  memset(&spv, 0, sizeof(spv));
+  spv.x_in = x_dev; spv.out = out_dev; spv.noise = noise_dev;
+  if (coef) {
+    spv.c_eps_in = coef->c_eps_in; spv.c_div = coef->c_div; spv.c_x0 = coef->c_x0; spv.c_eps_out = coef->c_eps_out;
+    spv.sigma = coef->sigma; spv.final_step = coef->final_step; spv.ddim_enabled = 1;
+  }
+  memcpy(hp, &spv, sizeof(spv));
+  int* hplan = reinterpret_cast<int*>(hp + off_plan);
+  for (int b = 0; b < nblk; ++b) { hplan[4 * b] = plan[3 * b]; hplan[4 * b + 1] = plan[3 * b + 1]; hplan[4 * b + 2] = plan[3 * b + 2]; hplan[4 * b + 3] = 0; }
+  memcpy(hp + off_tidx, t_index, (size_t)B * 4);
+  for (int l = 0; l < S; ++l) {
+    if (!te_host[l]) return fail(h, LDMB_ERR_INVALID, "te_host[%d] is NULL", l);
+    memcpy(hp + off_te[l], te_host[l], (size_t)n_t * u.levels[l].C * 4);
+  }
+  CK(cudaMemcpyAsync(sb, hp, total, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(u.staging_ev[slot], st));
+  u.staging_used[slot] = true;
+
+  // ---- launch: eagerly the first time a shape is seen (and when profiling), then capture once and replay the graph
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CK(cudaStreamIsCapturing(st, &cap));
+  UNetState::GraphEntry* ge = nullptr;
+  if (u.use_graphs && !h->prof_on && cap == cudaStreamCaptureStatusNone) {
+    for (auto& g : u.graphs)
+      if (g.B == B && g.Hs == Hs && g.Ws == Ws && g.n_t == n_t) { ge = &g; break; }
+    if (!ge) {
+      if (u.graphs.size() >= 16) { for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec); u.graphs.clear(); }
+      u.graphs.push_back({B, Hs, Ws, n_t, u.ws_epoch, nullptr, 0, 0});
+      ge = &u.graphs.back();
+    }
+    if (ge->epoch != u.ws_epoch) {     // a workspace moved since capture: the graph holds stale pointers
+      if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
+      ge->epoch = u.ws_epoch; ge->seen = 0;
+    }
+  }
+  if (ge && ge->exec) {
+    CK(cudaGraphLaunch(ge->exec, st));
+    h->launches += ge->launches;
+    return LDMB_OK;
+  }
+  if (ge && ge->seen >= 1) {
+    const long long l0 = h->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = issue_forward(h, B, Hs, Ws, n_t, te_dev, st);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || !graph) return fail(h, LDMB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ge->exec = nullptr; return fail(h, LDMB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    ge->launches = h->launches - l0;
+    CK(cudaGraphLaunch(ge->exec, st));
+    return LDMB_OK;
+  }
+  if (ge) ge->seen++;
+  return issue_forward(h, B, Hs, Ws, n_t, te_dev, st);
 }
 
 // =====================================================================================
@@ -1044,6 +1119,6 @@ extern "C" int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float
   if (!h || !x || !film || !out) return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CKLP(PK_NORM, (double)M * C * (4 + h->tsize()), launch_norm_film(x, film, nullptr, out, h->bf16(), M, C, HW, kNormEps, st));
+  CKLP(PK_NORM, (double)M * C * (4 + h->tsize()), launch_norm_film(x, film, nullptr, out, h->bf16(), M, C, HW, kNormEps, nullptr, st));
   return LDMB_OK;
 }

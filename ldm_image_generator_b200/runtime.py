@@ -88,6 +88,9 @@ class Handle:
     def set_force_simt(self, on: bool) -> None:
         self.check(self.lib.ldmb_set_force_simt(self.h, int(on)))
 
+    def set_use_graphs(self, on: bool) -> None:
+        self.check(self.lib.ldmb_set_use_graphs(self.h, int(on)))
+
     def device_fault(self) -> int:
         return int(self.lib.ldmb_check_device_fault(self.h, stream_ptr(self.device)))
 

@@ -80,3 +80,27 @@ def test_bad_inputs_raise_like_the_reference():
         model(torch.zeros(1, 8, 9, 9, device="cuda"), torch.zeros(1, dtype=torch.long))
     with pytest.raises(RuntimeError):      # no CPU fallback
         model(torch.zeros(1, 8, 8, 8), torch.zeros(1, dtype=torch.long))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_matches_eager_launches(precision):
+    """The CUDA-graph replay path (captured on the 2nd call of a shape, replayed afterwards) must produce exactly what
+    kernel-by-kernel launches produce, for changing plans (expert picks, skipped blocks), timesteps and DDIM scalars."""
+    from ldm_image_generator_b200 import _lib
+    cfg = R.UNetCfg(input_channels=8, stages=(2, 2), channels=(128, 256))
+    sd = R.make_unet_state(cfg, 31)
+    eager = build_unet(cfg, sd, precision)
+    graph = build_unet(cfg, sd, precision)
+    x = torch.randn(2, 8, 16, 16, device="cuda")
+    eager._prepare(x.device).set_use_graphs(False)
+    nblk = len(R.block_table(cfg))
+    for it in range(5):
+        random.seed(100 + it)
+        plan = R.draw_plan(nblk, training=(it % 2 == 1))
+        t = [999 - 200 * it] * 2
+        co = _lib.DdimCoef(0.9 + 0.01 * it, 0.5, 0.4, 0.3, 0.0, int(it == 4))
+        a = eager._run(x, t, coef=co, out=torch.empty_like(x), plan=plan)
+        b = graph._run(x, t, coef=co, out=torch.empty_like(x), plan=plan)
+        assert torch.equal(a, b), it
+    assert_no_fault(graph)
+    assert graph._handle.launches == eager._handle.launches
