@@ -89,6 +89,7 @@ struct UNetState {
   std::vector<GraphEntry> graphs;
   unsigned long long ws_epoch = 0;     // bumped whenever a workspace is reallocated (cached graphs hold raw pointers)
   bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy NULL stream)
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -267,6 +268,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
   release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
   if (u.staging) {
     cudaFreeHost(u.staging);
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
@@ -818,10 +820,11 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   }
   if (ge && ge->seen >= 1) {
     const long long l0 = h->launches;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = issue_forward(h, B, Hs, Ws, n_t, te_dev, st);
+    if (!u.cap_stream) CK(cudaStreamCreateWithFlags(&u.cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(u.cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = issue_forward(h, B, Hs, Ws, n_t, te_dev, u.cap_stream);
     cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    cudaError_t e = cudaStreamEndCapture(u.cap_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess || !graph) return fail(h, LDMB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(&ge->exec, graph, 0);
