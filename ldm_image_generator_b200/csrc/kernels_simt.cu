@@ -181,47 +181,59 @@ template <> struct Pack4<bf16> {
   }
 };
 
-template <typename T, int MAXV>
+// ROWS rows per warp are in flight at once (independent loads) so that narrow rows (C = 128: one float4 per lane)
+// still keep enough bytes in flight to cover HBM latency.
+template <typename T, int MAXV, int ROWS>
 __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict__ x, const float* __restrict__ film,
                                                         const int* __restrict__ t_index, T* __restrict__ out,
                                                         int M, int C, int HW, float eps, const int* __restrict__ skip) {
   if (skip != nullptr && *skip != 0) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps_per_grid) {
-    const float* xr = x + (long long)m * C;
-    float4 v[MAXV];
-    float sum = 0.f;
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; mb < M; mb += warps_per_grid * ROWS) {
+    float4 v[ROWS][MAXV];
+    float sum[ROWS];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (c < C) {
-        v[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
-        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int r = 0; r < ROWS; ++r) {
+      sum[r] = 0.f;
+      const int m = mb + r;
+      const float* xr = x + (long long)m * C;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (m < M && c < C) {
+          v[r][i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+          sum[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        }
       }
     }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (c < C) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    for (int r = 0; r < ROWS; ++r) {
+      const int m = mb + r;
+      if (m >= M) break;                               // warp-uniform
+      const float mean = warp_sum(sum[r]) / (float)C;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < C) {
+          v[r][i].x -= mean; v[r][i].y -= mean; v[r][i].z -= mean; v[r][i].w -= mean;
+          sq += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
+        }
       }
-    }
-    const float sd = sqrtf(warp_sum(sq) / (float)(C - 1) + eps);   // unbiased variance (modules.py:24)
-    const int trow = (t_index ? t_index[m / HW] : 0) * HW + m % HW;
-    const float* fr = film + (long long)trow * 2 * C;
-    T* orow = out + (long long)m * C;
+      const float sd = sqrtf(warp_sum(sq) / (float)(C - 1) + eps);   // unbiased variance (modules.py:24)
+      const int trow = (t_index ? t_index[m / HW] : 0) * HW + m % HW;
+      const float* fr = film + (long long)trow * 2 * C;
+      T* orow = out + (long long)m * C;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = i * 128 + lane * 4;
-      if (c < C) {
-        const float4 mu = __ldg(reinterpret_cast<const float4*>(fr + c));
-        const float4 bi = __ldg(reinterpret_cast<const float4*>(fr + C + c));
-        Pack4<T>::store(orow + c, (v[i].x / sd) * mu.x + bi.x, (v[i].y / sd) * mu.y + bi.y,
-                        (v[i].z / sd) * mu.z + bi.z, (v[i].w / sd) * mu.w + bi.w);
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < C) {
+          const float4 mu = __ldg(reinterpret_cast<const float4*>(fr + c));
+          const float4 bi = __ldg(reinterpret_cast<const float4*>(fr + C + c));
+          Pack4<T>::store(orow + c, (v[r][i].x / sd) * mu.x + bi.x, (v[r][i].y / sd) * mu.y + bi.y,
+                          (v[r][i].z / sd) * mu.z + bi.z, (v[r][i].w / sd) * mu.w + bi.w);
+        }
       }
     }
   }
@@ -408,57 +420,81 @@ __global__ void __launch_bounds__(64 * HC) window_attention_kernel(const T* __re
 // Few-channel pointwise convolutions at the NCHW fp32 boundary
 // =====================================================================================
 // in: NCHW fp32 [B, Cin, H*s, W*s], k = stride = s (s = 1: 1x1 conv).  out: [B*H*W, Cout] in TO.
+// One CTA per 64 pixels: the J = Cin*s*s inputs of each pixel and the [Cout][J] weights are staged in shared
+// memory (coalesced reads along w), then threads sweep (pixel, channel) pairs with coalesced NHWC stores.
+constexpr int kPixIn = 64;
 template <typename TO>
-__global__ void pointwise_in_kernel(const float* __restrict__ x, const StepParams* __restrict__ sp,
-                                    const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out,
-                                    int B, int Cin, int H, int W, int s, int Cout) {
+__global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restrict__ x, const StepParams* __restrict__ sp,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           TO* __restrict__ out, int B, int Cin, int H, int W, int s, int Cout) {
+  extern __shared__ float smem_in[];
   if (sp != nullptr) x = sp->x_in;
-  const long long total = (long long)B * H * W * Cout;
   const int J = Cin * s * s;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Cout);
-    long long t = i / Cout;
-    const int ww = (int)(t % W); t /= W;
-    const int hh = (int)(t % H);
-    const int b = (int)(t / H);
+  float* xs = smem_in;                    // [kPixIn][J + 1]
+  float* ws = smem_in + kPixIn * (J + 1); // [Cout][J]
+  const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * kPixIn;
+  for (int i = threadIdx.x; i < Cout * J; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < kPixIn * J; i += blockDim.x) {
+    const int p = i % kPixIn, j = i / kPixIn;           // consecutive threads -> consecutive pixels (contiguous along w)
+    const long long m = m0 + p;
+    float v = 0.f;
+    if (m < M) {
+      const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+      const int ci = j / (s * s), dy = (j / s) % s, dx = j % s;
+      v = x[(((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx];
+    }
+    xs[p * (J + 1) + j] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kPixIn * Cout; i += blockDim.x) {
+    const int p = i / Cout, co = i % Cout;
+    const long long m = m0 + p;
+    if (m >= M) break;
     float acc = bias[co];
-    const float* wr = w + (long long)co * J;
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int dy = 0; dy < s; ++dy)
-        for (int dx = 0; dx < s; ++dx)
-          acc = fmaf(x[(((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx],
-                     wr[(ci * s + dy) * s + dx], acc);
-    out[i] = from_f<TO>(acc);
+    const float* xr = xs + p * (J + 1);
+    const float* wr = ws + co * J;
+    for (int j = 0; j < J; ++j) acc = fmaf(xr[j], wr[j], acc);
+    out[m * Cout + co] = from_f<TO>(acc);
   }
 }
 
-// Reduce C channels of 32 consecutive NHWC pixels to J (<= 32) outputs each: warp w of 8 handles 4 pixels.
-// wmat is [C][J] (ConvTranspose layout) when w_cj, else [J][C] (Conv2d layout).  Result in smem e[J][32].
+// Few-output pointwise convolutions out of an NHWC tensor: J (<= 32) outputs per pixel.
+// One CTA per 32 pixels: the pixel rows are staged in shared memory in chunks of 128 channels (coalesced), thread
+// (pixel p = tid % 32, output j = tid / 32 + 8k) accumulates its dot product, results land in e[j][p].
+// wmat is [C][J] (ConvTranspose layout) when w_cj, else [J][C] (Conv2d layout).
 template <typename T>
-__device__ __forceinline__ void reduce_pixels_32(const T* __restrict__ x, long long m0, long long M, int C, int J,
-                                                 const float* __restrict__ wmat, bool w_cj, float (*e)[33]) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int pp = 0; pp < 4; ++pp) {
-    const int p = warp * 4 + pp;
-    const long long m = m0 + p;
-    for (int j0 = 0; j0 < J; j0 += 8) {
-      float part[8];
+__device__ __forceinline__ void pixel_dots_32(const T* __restrict__ x, long long m0, long long M, int C, int J,
+                                              const float* __restrict__ wmat, bool w_cj, float* xs /*[32][129]*/,
+                                              float* ws /*[128][J]*/, float (*e)[33]) {
+  const int p = threadIdx.x & 31, jg = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < C; c0 += 128) {
+    const int cn = min(128, C - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * cn; i += blockDim.x) {
+      const int pp = i / cn, c = i % cn;
+      const long long m = m0 + pp;
+      xs[pp * 129 + c] = m < M ? to_f(x[m * C + c0 + c]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < cn * J; i += blockDim.x) {
+      const int c = i / J, j = i % J;
+      ws[i] = w_cj ? wmat[(long long)(c0 + c) * J + j] : wmat[(long long)j * C + c0 + c];
+    }
+    __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) part[j] = 0.f;
-      if (m < M) {
-        for (int c = lane; c < C; c += 32) {
-          const float xv = to_f(x[m * C + c]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j0 + j < J) part[j] = fmaf(xv, w_cj ? wmat[(long long)c * J + j0 + j] : wmat[(long long)(j0 + j) * C + c], part[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = warp_sum(part[j]);
-        if (lane == 0 && j0 + j < J) e[j0 + j][p] = v;
+    for (int k = 0; k < 4; ++k) {
+      const int j = jg + 8 * k;
+      if (j < J) {
+        float a = acc[k];
+        for (int c = 0; c < cn; ++c) a = fmaf(xs[p * 129 + c], ws[c * J + j], a);
+        acc[k] = a;
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = jg + 8 * k;
+    if (j < J) e[j][p] = acc[k];
   }
 }
 
@@ -467,13 +503,15 @@ __global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ bias, const StepParams* __restrict__ sp,
                                                     int B, int Cin, int H, int W, int s, int C0) {
   __shared__ float e[32][33];
+  __shared__ float xs[32 * 129];
+  __shared__ float ws[128 * 32];
   const StepParams co = *sp;
   const float* __restrict__ xin = co.x_in;
   const float* __restrict__ noise = co.noise;
   float* __restrict__ out = co.out;
   const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * 32;
   const int J = Cin * s * s;
-  reduce_pixels_32<float>(x, m0, M, C0, J, w, true, e);
+  pixel_dots_32<float>(x, m0, M, C0, J, w, true, xs, ws, e);
   __syncthreads();
   for (int idx = threadIdx.x; idx < J * 32; idx += blockDim.x) {
     const int j = idx >> 5, p = idx & 31;
@@ -503,8 +541,10 @@ __global__ void __launch_bounds__(256) pointwise_out_kernel(const T* __restrict_
                                                             float* __restrict__ out, uint8_t* __restrict__ out_u8,
                                                             int B, int H, int W, int C, int Cout) {
   __shared__ float e[32][33];
+  __shared__ float xs[32 * 129];
+  __shared__ float ws[128 * 32];
   const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * 32;
-  reduce_pixels_32<T>(x, m0, M, C, Cout, w, false, e);
+  pixel_dots_32<T>(x, m0, M, C, Cout, w, false, xs, ws, e);
   __syncthreads();
   for (int idx = threadIdx.x; idx < Cout * 32; idx += blockDim.x) {
     const int j = idx >> 5, p = idx & 31;
@@ -561,28 +601,33 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
 
 cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
                         int s, int C0, cudaStream_t st) {
-  const long long total = (long long)B * H * W * C0;
-  pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
+  const long long M = (long long)B * H * W;
+  const int J = Cin * s * s;
+  const size_t smem = (size_t)(kPixIn * (J + 1) + C0 * J) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorNotSupported;
+  pointwise_in_kernel<float><<<(unsigned)((M + kPixIn - 1) / kPixIn), 256, smem, st>>>(nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }
 
 cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float* bias, void* out, bool is_bf16,
                                      int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
-  const long long total = (long long)B * H * W * Cout;
-  if (is_bf16) pointwise_in_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(x, nullptr, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
-  else pointwise_in_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, nullptr, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
+  const long long M = (long long)B * H * W;
+  const size_t smem = (size_t)(kPixIn * (Cin + 1) + Cout * Cin) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorNotSupported;
+  const unsigned grid = (unsigned)((M + kPixIn - 1) / kPixIn);
+  if (is_bf16) pointwise_in_kernel<bf16><<<grid, 256, smem, st>>>(x, nullptr, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
+  else pointwise_in_kernel<float><<<grid, 256, smem, st>>>(x, nullptr, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
                                       int HW, float eps, const int* skip, cudaStream_t st) {
-  const int blocks = grid_for((long long)M * 32, 256, 148 * 8);
-  if (C <= 128) norm_film_kernel<T, 1><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 256) norm_film_kernel<T, 2><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 512) norm_film_kernel<T, 4><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 1024) norm_film_kernel<T, 8><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 2048) norm_film_kernel<T, 16><<<blocks, 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  if (C <= 128) norm_film_kernel<T, 1, 4><<<grid_for((long long)((M + 3) / 4) * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 256) norm_film_kernel<T, 2, 2><<<grid_for((long long)((M + 1) / 2) * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 512) norm_film_kernel<T, 4, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 1024) norm_film_kernel<T, 8, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 2048) norm_film_kernel<T, 16, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
   else return cudaErrorNotSupported;
   return cudaGetLastError();
 }

@@ -79,10 +79,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int AMODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const GemmDesc dparam, const TcTiling tl, int* fault) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault) {
   using Cfg = TcCfg<BN>;
-  GemmDesc d = dparam;
-  if (resolve_plan(d)) return;     // block skipped this step: uniform exit before any barrier / TMEM allocation
+  // expert rows of the (up to 4) selection slots, resolved from the device-side plan when there is one
+  int srow0 = d.sel_rows[0], srow1 = d.sel_rows[1], srow2 = d.sel_rows[2], srow3 = d.sel_rows[3];
+  if (d.plan != nullptr) {
+    if (d.plan[0] != 0) return;    // block skipped this step: uniform exit before any barrier / TMEM allocation
+    if (d.sel != 0) { srow0 = 0; srow1 = (1 + d.plan[1]) * d.sel_stride; srow2 = (1 + d.plan[2]) * d.sel_stride; srow3 = 5 * d.sel_stride; }
+  }
+  auto srow = [&](int q) { return q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3)); };
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -145,8 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
           }
           int brow, bcol = kk;
-          if (d.sel == 2) { brow = d.sel_rows[kk / d.sel_span] + n0; bcol = kk % d.sel_span; }
-          else if (d.sel == 1) brow = d.sel_rows[n0 / d.sel_span] + n0 % d.sel_span;
+          if (d.sel == 2) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
+          else if (d.sel == 1) brow = srow(n0 / d.sel_span) + n0 % d.sel_span;
           else brow = n0;
           ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow + (int)(z * d.w_row_b));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -197,7 +202,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
-      for (int c = et; c < BN; c += 32 * kEpiWarps) sb[c] = (n0 + c < d.N) ? bias_of_col(d, z, n0 + c) : 0.f;
+      for (int c = et; c < BN; c += 32 * kEpiWarps) {
+        const int n = n0 + c;
+        float bv = 0.f;
+        if (n < d.N && d.bias != nullptr) {
+          const float* bp = d.bias + z * d.bias_off_b;
+          if (d.sel == 2) { for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; }
+          else if (d.sel == 1) bv = bp[srow(n / d.sel_span) + n % d.sel_span];
+          else bv = bp[n];
+        }
+        sb[c] = bv;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
       ptx::tc_fence_after();

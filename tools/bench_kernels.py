@@ -11,16 +11,25 @@ from ldm_image_generator_b200 import runtime  # noqa: E402
 
 
 def timeit(fn, iters=20):
-    for _ in range(3):
-        fn(0)
+    """Average GPU time per launch: `iters` launches captured in one CUDA graph (no host launch overhead)."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for i in range(iters):
+            fn(i)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i)
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3   # us
+    return e0.elapsed_time(e1) / (3 * iters) * 1e3   # us
 
 
 def main():
