@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 typedef __nv_bfloat16 bf16;
 
@@ -60,6 +61,29 @@ __device__ __forceinline__ bool resolve_plan(GemmDesc& d) {
     d.sel_rows[3] = 5 * d.sel_stride;
   }
   return false;
+}
+
+// ---- programmatic dependent launch (PDL): every kernel of the library is launched with the stream-serialization
+// attribute and starts with pdl_wait(), so its launch latency / prologue overlaps the tail of the previous kernel.
+// griddepcontrol.wait blocks until the preceding kernel has completed and its writes are visible; it is a no-op
+// for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern bool g_ldmb_pdl;   // host toggle (LDMB_NO_PDL=1 disables), defined in kernels_simt.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_ldmb_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -4,6 +4,9 @@
 #include "kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
+
+bool g_ldmb_pdl = getenv("LDMB_NO_PDL") == nullptr;
 
 namespace {
 
@@ -14,6 +17,7 @@ namespace {
 // =====================================================================================
 template <typename T, int AMODE, bool GLU>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc dparam) {
+  pdl_wait();
   constexpr int BM = 64, BN = 64, BK = 16, NW = GLU ? 2 : 1;
   GemmDesc d = dparam;
   if (resolve_plan(d)) return;
@@ -129,11 +133,11 @@ cudaError_t gemm_simt_dispatch(const GemmDesc& d, cudaStream_t s) {
   dim3 grid((NL + 63) / 64, (d.M + 63) / 64, d.batch > 0 ? d.batch : 1);
   if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
   if (d.amode == AM_ROWS) {
-    if (glu) gemm_simt_kernel<T, AM_ROWS, true><<<grid, 256, 0, s>>>(d);
-    else gemm_simt_kernel<T, AM_ROWS, false><<<grid, 256, 0, s>>>(d);
+    if (glu) launch_k((gemm_simt_kernel<T, AM_ROWS, true>), grid, 256, 0, s, d);
+    else launch_k((gemm_simt_kernel<T, AM_ROWS, false>), grid, 256, 0, s, d);
   } else {
     if (glu) return cudaErrorNotSupported;
-    gemm_simt_kernel<T, AM_CONV3, false><<<grid, 256, 0, s>>>(d);
+    launch_k((gemm_simt_kernel<T, AM_CONV3, false>), grid, 256, 0, s, d);
   }
   return cudaGetLastError();
 }
@@ -144,6 +148,7 @@ cudaError_t gemm_simt_dispatch(const GemmDesc& d, cudaStream_t s) {
 struct Repack4 { int dims[4]; long long ss[4]; long long ds[4]; };
 template <typename T>
 __global__ void repack_kernel(const float* __restrict__ src, T* __restrict__ dst, Repack4 r, long long total) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
     const int i3 = t % r.dims[3]; t /= r.dims[3];
@@ -187,6 +192,7 @@ template <typename T, int MAXV, int ROWS>
 __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict__ x, const float* __restrict__ film,
                                                         const int* __restrict__ t_index, T* __restrict__ out,
                                                         int M, int C, int HW, float eps, const int* __restrict__ skip) {
+  pdl_wait();
   if (skip != nullptr && *skip != 0) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict_
 template <typename T>
 __global__ void emb_build_kernel(const float* __restrict__ pe, const float* __restrict__ te, T* __restrict__ emb,
                                  int n_t, int HW, int C) {
+  pdl_wait();
   const long long total = (long long)n_t * HW * 2 * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (2 * C));
@@ -253,6 +260,7 @@ __global__ void emb_build_kernel(const float* __restrict__ pe, const float* __re
 
 template <typename TI, typename TO>
 __global__ void pool2_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C) {
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -269,11 +277,13 @@ __global__ void pool2_kernel(const TI* __restrict__ x, TO* __restrict__ out, int
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = from_f<T>(x[i]);
 }
 
 __global__ void upsample_add_kernel(float* __restrict__ x, const float* __restrict__ ylow, int B, int H, int W, int C4) {
+  pdl_wait();
   // C4 = C / 4 (float4 lanes)
   const long long total = (long long)B * H * W * C4;
   float4* x4 = reinterpret_cast<float4*>(x);
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(64 * HC) window_attention_kernel(const T* __re
                                                                  const float* __restrict__ b_in, T* __restrict__ att,
                                                                  long long ldo, int H, int W, int C, int wh, int ww,
                                                                  int shift, int Hp, int Wp, const int* __restrict__ skip) {
+  pdl_wait();
   if (skip != nullptr && *skip != 0) return;
   constexpr int VN = Vec16<T>::N;
   constexpr int ROW = HC * D;                     // channels of this head chunk
@@ -427,6 +438,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restrict__ x, const StepParams* __restrict__ sp,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            TO* __restrict__ out, int B, int Cin, int H, int W, int s, int Cout) {
+  pdl_wait();
   extern __shared__ float smem_in[];
   if (sp != nullptr) x = sp->x_in;
   const int J = Cin * s * s;
@@ -502,6 +514,7 @@ __device__ __forceinline__ void pixel_dots_32(const T* __restrict__ x, long long
 __global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, const StepParams* __restrict__ sp,
                                                     int B, int Cin, int H, int W, int s, int C0) {
+  pdl_wait();
   __shared__ float e[32][33];
   __shared__ float xs[32 * 129];
   __shared__ float ws[128 * 32];
@@ -540,6 +553,7 @@ __global__ void __launch_bounds__(256) pointwise_out_kernel(const T* __restrict_
                                                             const float* __restrict__ bias, const float* __restrict__ prev,
                                                             float* __restrict__ out, uint8_t* __restrict__ out_u8,
                                                             int B, int H, int W, int C, int Cout) {
+  pdl_wait();
   __shared__ float e[32][33];
   __shared__ float xs[32 * 129];
   __shared__ float ws[128 * 32];
@@ -594,8 +608,8 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
   long long total = 1;
   for (int i = 0; i < 4; ++i) { r.dims[i] = dims[i]; r.ss[i] = sstr[i]; r.ds[i] = dstr[i]; total *= dims[i]; }
   if (total == 0) return cudaSuccess;
-  if (dst_bf16) repack_kernel<bf16><<<grid_for(total, 256), 256, 0, s>>>(src, (bf16*)dst, r, total);
-  else repack_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(src, (float*)dst, r, total);
+  if (dst_bf16) launch_k((repack_kernel<bf16>), grid_for(total, 256), 256, 0, s, src, (bf16*)dst, r, total);
+  else launch_k((repack_kernel<float>), grid_for(total, 256), 256, 0, s, src, (float*)dst, r, total);
   return cudaGetLastError();
 }
 
@@ -605,7 +619,7 @@ cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias,
   const int J = Cin * s * s;
   const size_t smem = (size_t)(kPixIn * (J + 1) + C0 * J) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorNotSupported;
-  pointwise_in_kernel<float><<<(unsigned)((M + kPixIn - 1) / kPixIn), 256, smem, st>>>(nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
+  launch_k((pointwise_in_kernel<float>), (unsigned)((M + kPixIn - 1) / kPixIn), 256, smem, st, nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }
 
@@ -615,19 +629,19 @@ cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float
   const size_t smem = (size_t)(kPixIn * (Cin + 1) + Cout * Cin) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorNotSupported;
   const unsigned grid = (unsigned)((M + kPixIn - 1) / kPixIn);
-  if (is_bf16) pointwise_in_kernel<bf16><<<grid, 256, smem, st>>>(x, nullptr, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
-  else pointwise_in_kernel<float><<<grid, 256, smem, st>>>(x, nullptr, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
+  if (is_bf16) launch_k((pointwise_in_kernel<bf16>), grid, 256, smem, st, x, nullptr, w, bias, (bf16*)out, B, Cin, H, W, 1, Cout);
+  else launch_k((pointwise_in_kernel<float>), grid, 256, smem, st, x, nullptr, w, bias, (float*)out, B, Cin, H, W, 1, Cout);
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
                                       int HW, float eps, const int* skip, cudaStream_t st) {
-  if (C <= 128) norm_film_kernel<T, 1, 4><<<grid_for((long long)((M + 3) / 4) * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 256) norm_film_kernel<T, 2, 2><<<grid_for((long long)((M + 1) / 2) * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 512) norm_film_kernel<T, 4, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 1024) norm_film_kernel<T, 8, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 2048) norm_film_kernel<T, 16, 1><<<grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st>>>(x, film, t_index, out, M, C, HW, eps, skip);
+  if (C <= 128) launch_k((norm_film_kernel<T, 1, 4>), grid_for((long long)((M + 3) / 4) * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 256) launch_k((norm_film_kernel<T, 2, 2>), grid_for((long long)((M + 1) / 2) * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 512) launch_k((norm_film_kernel<T, 4, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 1024) launch_k((norm_film_kernel<T, 8, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+  else if (C <= 2048) launch_k((norm_film_kernel<T, 16, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
   else return cudaErrorNotSupported;
   return cudaGetLastError();
 }
@@ -642,35 +656,35 @@ cudaError_t launch_norm_film(const float* x, const float* film, const int* t_ind
 cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool is_bf16, int n_t, int HW, int C,
                              cudaStream_t st) {
   const long long total = (long long)n_t * HW * 2 * C;
-  if (is_bf16) emb_build_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(pe, te, (bf16*)emb, n_t, HW, C);
-  else emb_build_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(pe, te, (float*)emb, n_t, HW, C);
+  if (is_bf16) launch_k((emb_build_kernel<bf16>), grid_for(total, 256), 256, 0, st, pe, te, (bf16*)emb, n_t, HW, C);
+  else launch_k((emb_build_kernel<float>), grid_for(total, 256), 256, 0, st, pe, te, (float*)emb, n_t, HW, C);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pool_cast(const float* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * C;
-  if (is_bf16) pool2_kernel<float, bf16><<<grid_for(total, 256), 256, 0, st>>>(x, (bf16*)out, B, H, W, C);
-  else pool2_kernel<float, float><<<grid_for(total, 256), 256, 0, st>>>(x, (float*)out, B, H, W, C);
+  if (is_bf16) launch_k((pool2_kernel<float, bf16>), grid_for(total, 256), 256, 0, st, x, (bf16*)out, B, H, W, C);
+  else launch_k((pool2_kernel<float, float>), grid_for(total, 256), 256, 0, st, x, (float*)out, B, H, W, C);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pool_t(const void* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * C;
-  if (is_bf16) pool2_kernel<bf16, bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)out, B, H, W, C);
-  else pool2_kernel<float, float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C);
+  if (is_bf16) launch_k((pool2_kernel<bf16, bf16>), grid_for(total, 256), 256, 0, st, (const bf16*)x, (bf16*)out, B, H, W, C);
+  else launch_k((pool2_kernel<float, float>), grid_for(total, 256), 256, 0, st, (const float*)x, (float*)out, B, H, W, C);
   return cudaGetLastError();
 }
 
 cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cudaStream_t st) {
-  if (is_bf16) cast_kernel<bf16><<<grid_for(n, 256), 256, 0, st>>>(x, (bf16*)out, n);
-  else cast_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(x, (float*)out, n);
+  if (is_bf16) launch_k((cast_kernel<bf16>), grid_for(n, 256), 256, 0, st, x, (bf16*)out, n);
+  else launch_k((cast_kernel<float>), grid_for(n, 256), 256, 0, st, x, (float*)out, n);
   return cudaGetLastError();
 }
 
 cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st) {
   if (C % 4 != 0) return cudaErrorNotSupported;
   const long long total = (long long)B * H * W * (C / 4);
-  upsample_add_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, ylow, B, H, W, C / 4);
+  launch_k((upsample_add_kernel), grid_for(total, 256), 256, 0, st, x, ylow, B, H, W, C / 4);
   return cudaGetLastError();
 }
 
@@ -683,7 +697,7 @@ static cudaError_t window_attention_launch(const void* qkv, const void* xm, cons
   dim3 grid(B * (Hp / win_h) * (Wp / win_w), heads / HC);
   if (grid.y > 65535u) return cudaErrorNotSupported;
   int threads = ((L * HC + 31) / 32) * 32;
-  window_attention_kernel<T, 32, HC><<<grid, threads, 0, st>>>((const T*)qkv, (const T*)xm, b_in, (T*)att, ldo, H, W, C,
+  launch_k((window_attention_kernel<T, 32, HC>), grid, threads, 0, st, (const T*)qkv, (const T*)xm, b_in, (T*)att, ldo, H, W, C,
                                                               win_h, win_w, shift, Hp, Wp, skip);
   return cudaGetLastError();
 }
@@ -706,7 +720,7 @@ cudaError_t launch_final(const float* x, const float* w, const float* bias, cons
                          int W, int s, int C0, cudaStream_t st) {
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
-  final_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(x, w, bias, sp, B, Cin, H, W, s, C0);
+  launch_k((final_kernel), (unsigned)((M + 31) / 32), 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }
 
@@ -716,7 +730,7 @@ cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* 
   if (Cout > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
   const unsigned grid = (unsigned)((M + 31) / 32);
-  if (is_bf16) pointwise_out_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
-  else pointwise_out_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+  if (is_bf16) launch_k((pointwise_out_kernel<bf16>), grid, 256, 0, st, (const bf16*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+  else launch_k((pointwise_out_kernel<float>), grid, 256, 0, st, (const float*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
   return cudaGetLastError();
 }

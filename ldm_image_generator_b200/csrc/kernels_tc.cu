@@ -81,13 +81,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault) {
   using Cfg = TcCfg<BN>;
-  // expert rows of the (up to 4) selection slots, resolved from the device-side plan when there is one
-  int srow0 = d.sel_rows[0], srow1 = d.sel_rows[1], srow2 = d.sel_rows[2], srow3 = d.sel_rows[3];
-  if (d.plan != nullptr) {
-    if (d.plan[0] != 0) return;    // block skipped this step: uniform exit before any barrier / TMEM allocation
-    if (d.sel != 0) { srow0 = 0; srow1 = (1 + d.plan[1]) * d.sel_stride; srow2 = (1 + d.plan[2]) * d.sel_stride; srow3 = 5 * d.sel_stride; }
-  }
-  auto srow = [&](int q) { return q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3)); };
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,12 +113,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_z = tl.m_tiles * tl.n_tiles;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail.
+  pdl_wait();
+  // expert rows of the (up to 4) selection slots, resolved from the device-side plan when there is one
+  int srow0 = d.sel_rows[0], srow1 = d.sel_rows[1], srow2 = d.sel_rows[2], srow3 = d.sel_rows[3];
+  bool skip_block = false;
+  if (d.plan != nullptr) {
+    skip_block = d.plan[0] != 0;   // stochastic depth skipped this block for this step (uniform over the grid)
+    if (d.sel != 0) { srow0 = 0; srow1 = (1 + d.plan[1]) * d.sel_stride; srow2 = (1 + d.plan[2]) * d.sel_stride; srow3 = 5 * d.sel_stride; }
+  }
+  auto srow = [&](int q) { return q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3)); };
+  const int total_tiles = skip_block ? 0 : tl.total;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int z = t / tiles_per_z, rem = t % tiles_per_z;
         const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
         const int m0 = mt * BM, n0 = nt * BN;
@@ -164,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -197,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
-    for (int t = blockIdx.x; t < tl.total; t += gridDim.x) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int z = t / tiles_per_z, rem = t % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
@@ -536,8 +540,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
     attr_set = true;
   }
   const int grid = tl.total < ctx->num_sms ? tl.total : ctx->num_sms;
-  gemm_tc_kernel<BN, AMODE><<<grid, kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmO, d, tl, ctx->fault_dev);
-  return cudaGetLastError();
+  return launch_k((gemm_tc_kernel<BN, AMODE>), dim3(grid), dim3(kThreads), (size_t)Cfg::SMEM_BYTES, s, tmA, tmB, tmO, d, tl, ctx->fault_dev);
 }
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
