@@ -106,6 +106,12 @@ int64_t ldmb_launch_count(const ldmb_handle* h);
 /* 0, or the watchdog code a tcgen05 pipeline wrote when an mbarrier wait timed out (device read; synchronises). */
 int ldmb_check_device_fault(ldmb_handle* h, void* stream);
 
+/* Debug: %globaltimer stamps inside the tcgen05 kernel.  stamps_host == NULL: enable/disable recording.
+ * Otherwise copies 16 int64 stamps per CTA of the most recent tcgen05 launch (synchronises) and returns the CTA count:
+ * 0 entry, 1 setup done, 2 previous kernel complete, 3 first TMA issued, 4 first operands landed, 5 all MMAs issued,
+ * 6 first accumulator ready, 7 latest accumulator ready, 8 epilogue done, 9 exit. */
+int ldmb_debug_tc_trace(ldmb_handle* h, int enable, int64_t* stamps_host, int max_ctas);
+
 /* Per-kernel-class device timing for roofline reports (bench.py).  Between begin and end every launch is
  * bracketed by CUDA events on its stream; end synchronises and returns, per class, the summed event time (ms),
  * the summed algorithmic work (FLOPs for the GEMM/conv classes, bytes for the HBM-bound ones) and the launch count.

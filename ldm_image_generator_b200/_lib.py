@@ -48,6 +48,7 @@ SIGNATURES = {
     "ldmb_set_use_graphs": (C.c_int, [_H, C.c_int]),
     "ldmb_launch_count": (C.c_int64, [_H]),
     "ldmb_check_device_fault": (C.c_int, [_H, _P]),
+    "ldmb_debug_tc_trace": (C.c_int, [_H, C.c_int, _I64P, C.c_int]),
     "ldmb_profile_begin": (C.c_int, [_H]),
     "ldmb_profile_end": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64P]),
     "ldmb_unet_configure": (C.c_int, [_H, C.POINTER(UNetConfig)]),

@@ -16,6 +16,7 @@
 // Every mbarrier wait carries a watchdog: a stuck pipeline sets a fault flag and drains instead of hanging the GPU.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -30,7 +31,9 @@ struct TcContext {
   int num_sms;
   int* fault_dev;
   int device;
+  long long* trace_dev;   // debug: per-CTA %globaltimer stamps of the last launch (NULL unless enabled)
 };
+constexpr int kTraceSlots = 16;
 
 namespace {
 
@@ -45,16 +48,22 @@ struct TcTiling {
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
 };
 
-template <int BN> struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+// CG = CTAs per tile: 1 (128 x BN per CTA) or 2 (a CTA pair computes 256 x BN with cta_group::2; each CTA stages its
+// own 128 rows of A and BN/2 rows of B, so the pair moves 2/3 of the L2->SM bytes per FLOP of two independent CTAs).
+template <int BN, int CG> struct TcCfg {
+  static constexpr int B_ROWS = BN / CG;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLAB_BYTES = 32 * 128;               // one warp's 32 rows x 128 B
   static constexpr int STAGING_BYTES = kEpiWarps * 2 * SLAB_BYTES;   // per epilogue warp, double buffered
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
+  static constexpr int FIXED_BYTES = 1024 + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
+  static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;       // 227 KB of dynamic smem per CTA
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = FIXED_BYTES + STAGES * STAGE_BYTES;
 };
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
@@ -71,17 +80,27 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, volatil
   }
 }
 
+__device__ __forceinline__ void trace_stamp(long long* trace, int slot) {
+  if (trace != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[blockIdx.x * kTraceSlots + slot] = t;
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int AMODE>
+template <int BN, int AMODE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault) {
-  using Cfg = TcCfg<BN>;
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault, long long* trace) {
+  using Cfg = TcCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;   // position in the CTA pair
+  const bool leader = rank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = tiles + STAGES * Cfg::STAGE_BYTES;      // 1024-aligned (every stage is a multiple of 1024 B)
@@ -95,9 +114,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0) trace_stamp(trace, 0);                 // kernel entry
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kEpiWarps * CG); }
     *s_abort = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
@@ -105,16 +125,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tl.tma_out) ptx::prefetch_tensormap(&tmO);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_z = tl.m_tiles * tl.n_tiles;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail.
+  if (threadIdx.x == 0) trace_stamp(trace, 1);                 // setup done
   pdl_wait();
+  if (threadIdx.x == 0) trace_stamp(trace, 2);                 // previous kernel complete
   // expert rows of the (up to 4) selection slots, resolved from the device-side plan when there is one
   int srow0 = d.sel_rows[0], srow1 = d.sel_rows[1], srow2 = d.sel_rows[2], srow3 = d.sel_rows[3];
   bool skip_block = false;
@@ -129,10 +152,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
         const int z = t / tiles_per_z, rem = t % tiles_per_z;
         const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
-        const int m0 = mt * BM, n0 = nt * BN;
+        const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
         int b0 = 0, h0 = 0, w0 = 0;
         if (AMODE == AM_CONV3) {
           const int hw = d.cH * d.cW;
@@ -145,19 +168,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
           const int kk = kb * BK;
           if (AMODE == AM_ROWS) {
-            ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
+            if (CG == 2) ptx::tma_load_2d_2sm(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
+            else ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
           } else {
             const int tap = kk / d.cC, c0 = kk % d.cC;
-            ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+            if (CG == 2) ptx::tma_load_4d_2sm(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+            else ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
           }
           int brow, bcol = kk;
           if (d.sel == 2) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
           else if (d.sel == 1) brow = srow(n0 / d.sel_span) + n0 % d.sel_span;
           else brow = n0;
-          ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow + (int)(z * d.w_row_b));
+          brow += (int)(z * d.w_row_b) + (int)rank * Cfg::B_ROWS;      // this CTA's share of the tile's weight rows
+          if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
+          else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
+          if (t == (int)(blockIdx.x / CG) && kb == 0) trace_stamp(trace, 3);   // first loads issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -165,29 +193,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < tl.num_kb; ++kb) {
           wait_bar(&full[stage], phase, s_abort, fault, 3);
+          if (t == (int)(blockIdx.x / CG) && kb == 0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
-          ptx::umma_commit(&empty[stage]);        // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k) {
+            if (CG == 2) ptx::umma_f16_2sm(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
+                                           (kb | k) != 0 ? 1u : 0u);
+            else ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+          }
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull[as]);             // accumulator complete -> epilogue
+        if (CG == 2) ptx::umma_commit_2sm(&tfull[as], 3); else ptx::umma_commit(&tfull[as]);   // accumulator complete -> epilogue(s)
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
+      trace_stamp(trace, 5);                                           // all MMAs issued
     }
     __syncwarp();
   } else {
@@ -201,10 +235,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
       const int z = t / tiles_per_z, rem = t % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
-      const int m0 = mt * BM, n0 = nt * BN;
+      const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
@@ -219,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
+      if (threadIdx.x == 64) trace_stamp(trace, t == (int)(blockIdx.x / CG) ? 6 : 7);   // first / latest accumulator ready
       ptx::tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < d.M;
@@ -418,16 +453,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      if (lane == 0) { if (CG == 2) ptx::mbar_arrive_leader(&tempty[as]); else ptx::mbar_arrive(&tempty[as]); }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
     if (tl.tma_out && lane == 0) ptx::bulk_wait<0>();       // all of this warp's stores have landed
     __syncwarp();
+    if (threadIdx.x == 64) trace_stamp(trace, 8);            // epilogue done
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CG == 2) ptx::cluster_sync();      // the peer has stopped reading our smem / signalling our barriers
+  if (warp == 1) { if (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (threadIdx.x == 0) trace_stamp(trace, 9);               // exit
 }
 
 bool conv_tile(const GemmDesc& d, int& TW, int& TH, int& TB) {
@@ -459,9 +497,9 @@ int pick_bn(const GemmDesc& d, int num_sms) {
     if (d.epi == EPI_REGLU && bn < 128) return false;
     return true;
   };
-  if (ok(256) && m_tiles * (d.N / 256) * batch >= 2LL * num_sms) return 256;
+  (void)m_tiles; (void)batch; (void)num_sms;
+  if (ok(256)) return 256;       // the widest tile: L2->SM bytes per FLOP decide the main-loop rate
   if (ok(128)) return 128;
-  if (ok(256)) return 256;
   if (ok(64)) return 64;
   return 0;
 }
@@ -492,6 +530,7 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   ctx->device = device;
   ctx->encode = nullptr;
   ctx->fault_dev = nullptr;
+  ctx->trace_dev = nullptr;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -519,7 +558,26 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
 void tc_context_destroy(TcContext* ctx) {
   if (!ctx) return;
   if (ctx->fault_dev) cudaFree(ctx->fault_dev);
+  if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   delete ctx;
+}
+
+int tc_trace_enable(TcContext* ctx, int on) {
+  if (on && !ctx->trace_dev) {
+    if (cudaMalloc(&ctx->trace_dev, sizeof(long long) * kTraceSlots * 256) != cudaSuccess) return -1;
+    cudaMemset(ctx->trace_dev, 0, sizeof(long long) * kTraceSlots * 256);
+  } else if (!on && ctx->trace_dev) {
+    cudaFree(ctx->trace_dev);
+    ctx->trace_dev = nullptr;
+  }
+  return 0;
+}
+int tc_trace_read(TcContext* ctx, long long* host, int max_ctas) {
+  if (!ctx->trace_dev) return -1;
+  const int n = max_ctas < 256 ? max_ctas : 256;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * kTraceSlots * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
 }
 
 int tc_read_fault(TcContext* ctx, cudaStream_t s) {
@@ -529,26 +587,47 @@ int tc_read_fault(TcContext* ctx, cudaStream_t s) {
   return v;
 }
 
-template <int BN, int AMODE>
+template <int BN, int AMODE, int CG>
 static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                                   const GemmDesc& d, const TcTiling& tl, cudaStream_t s) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = tl.total < ctx->num_sms ? tl.total : ctx->num_sms;
-  return launch_k((gemm_tc_kernel<BN, AMODE>), dim3(grid), dim3(kThreads), (size_t)Cfg::SMEM_BYTES, s, tmA, tmB, tmO, d, tl, ctx->fault_dev);
+  int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  if (CG == 2) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
+  cfg.attrs = at; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMODE, CG>, tmA, tmB, tmO, d, tl, ctx->fault_dev, ctx->trace_dev);
 }
+
+template <int AMODE, int CG>
+static cudaError_t launch_tc_bn(TcContext* ctx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                const GemmDesc& d, const TcTiling& tl, cudaStream_t s) {
+  if (bn == 256) return launch_tc_inst<256, AMODE, CG>(ctx, tmA, tmB, tmO, d, tl, s);
+  if (bn == 128) return launch_tc_inst<128, AMODE, CG>(ctx, tmA, tmB, tmO, d, tl, s);
+  return launch_tc_inst<64, AMODE, CG>(ctx, tmA, tmB, tmO, d, tl, s);
+}
+
+static int g_tc_force_cg = getenv("LDMB_TC_CG") ? atoi(getenv("LDMB_TC_CG")) : 0;   // debug: 1 or 2 forces the CTA-group size
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   if (!tc_supported(d)) return cudaErrorNotSupported;
   const int bn = pick_bn(d, ctx->num_sms);
   const int batch = d.batch > 0 ? d.batch : 1;
+  // CTA pairs (cta_group::2) whenever there are at least two 128-row tiles to pair up
+  int cg = d.M > BM ? 2 : 1;
+  if (g_tc_force_cg == 1 || g_tc_force_cg == 2) cg = g_tc_force_cg;
   TcTiling tl;
-  tl.m_tiles = (d.M + BM - 1) / BM;
+  tl.m_tiles = (d.M + BM * cg - 1) / (BM * cg);
   tl.n_tiles = (d.N + bn - 1) / bn;
   tl.num_kb = d.K / BK;
   tl.total = tl.m_tiles * tl.n_tiles * batch;
@@ -586,7 +665,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
     rows += (long long)(batch - 1) * d.w_row_b;
     const cuuint64_t gdim[2] = {(cuuint64_t)d.ldw, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)d.ldw * 2};
-    const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)(bn / cg)};
     r = ctx->encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.W), gdim, gstr, box, ones,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -620,12 +699,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
       tl.tma_out = 1;
     }
   }
-  if (d.amode == AM_ROWS) {
-    if (bn == 256) return launch_tc_inst<256, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
-    if (bn == 128) return launch_tc_inst<128, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
-    return launch_tc_inst<64, AM_ROWS>(ctx, tmA, tmB, tmO, d, tl, s);
-  }
-  if (bn == 256) return launch_tc_inst<256, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
-  if (bn == 128) return launch_tc_inst<128, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
-  return launch_tc_inst<64, AM_CONV3>(ctx, tmA, tmB, tmO, d, tl, s);
+  if (d.amode == AM_ROWS)
+    return cg == 2 ? launch_tc_bn<AM_ROWS, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_ROWS, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);
+  return cg == 2 ? launch_tc_bn<AM_CONV3, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_CONV3, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);
 }

@@ -283,6 +283,11 @@ extern "C" const char* ldmb_last_error(const ldmb_handle* h) { return h ? h->err
 extern "C" int ldmb_precision_of(const ldmb_handle* h) { return h ? h->precision : -1; }
 extern "C" int ldmb_set_force_simt(ldmb_handle* h, int on) { if (!h) return LDMB_ERR_INVALID; h->force_simt = on != 0; return LDMB_OK; }
 extern "C" int64_t ldmb_launch_count(const ldmb_handle* h) { return h ? h->launches : 0; }
+extern "C" int ldmb_debug_tc_trace(ldmb_handle* h, int enable, int64_t* stamps_host, int max_ctas) {
+  if (!h) return -1;
+  if (stamps_host == nullptr) return tc_trace_enable(h->tc, enable);
+  return tc_trace_read(h->tc, reinterpret_cast<long long*>(stamps_host), max_ctas);
+}
 extern "C" int ldmb_profile_begin(ldmb_handle* h) {
   if (!h) return LDMB_ERR_INVALID;
   h->prof.clear();

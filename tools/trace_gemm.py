@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Where does the time go inside one tcgen05 GEMM launch?  Per-CTA %globaltimer stamps (debug hook)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from ldm_image_generator_b200 import runtime  # noqa: E402
+
+NAMES = ["entry", "setup", "prev_done", "tma0", "data0", "mma_end", "acc0", "accN", "epi_end", "exit"]
+
+
+def main():
+    h = runtime.Handle(torch.device("cuda", 0), "bf16")
+    shapes = [(4096, 1536, 512), (4096, 3072, 512), (65536, 768, 128), (4096, 512, 1536), (1024, 6144, 1024), (16384, 1536, 256)]
+    if len(sys.argv) > 3:
+        shapes = [tuple(int(v) for v in sys.argv[1:4])]
+    for (M, N, K) in shapes:
+        A = torch.randn(M, K, device="cuda").bfloat16(); W = torch.randn(N, K, device="cuda").bfloat16()
+        bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        for _ in range(3):
+            h.gemm(A, W, bias, out, M, N, K)
+        torch.cuda.synchronize()
+        h.lib.ldmb_debug_tc_trace(h.h, 1, None, 0)
+        # back-to-back launches so the traced one sees a busy predecessor
+        for _ in range(4):
+            h.gemm(A, W, bias, out, M, N, K)
+        buf = (C.c_int64 * (16 * 256))()
+        n = h.lib.ldmb_debug_tc_trace(h.h, 1, buf, 256)
+        h.lib.ldmb_debug_tc_trace(h.h, 0, None, 0)
+        a = np.frombuffer(buf, dtype=np.int64).reshape(256, 16)[:148, :10].astype(np.float64)
+        a = a[a[:, 0] > 0]
+        t0 = a[:, 0].min()
+        rel = (a - t0) / 1000.0
+        print(f"M={M} N={N} K={K}: {len(a)} CTAs, kernel span {rel[:, 9].max():.2f} us")
+        for i, nm in enumerate(NAMES):
+            col = rel[:, i]
+            print(f"   {nm:10s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f} us")
+
+
+if __name__ == "__main__":
+    main()
