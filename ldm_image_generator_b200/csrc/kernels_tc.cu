@@ -685,7 +685,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
     long long rows = d.M;
     if (ok && batch > 1) {
       if (d.out_off_b + out_n <= d.ldo && d.out_off_b * (batch - 1) + out_n <= d.ldo) tl.out_col_b = (int)d.out_off_b;
-      else if (d.out_off_b % d.ldo == 0 && d.M % BM == 0) { tl.out_row_b = (int)(d.out_off_b / d.ldo); rows = (long long)tl.out_row_b * (batch - 1) + d.M; }
+      else if (d.out_off_b % d.ldo == 0 && d.M % (BM * cg) == 0) {   /* no tile may spill into the next batch's rows */ tl.out_row_b = (int)(d.out_off_b / d.ldo); rows = (long long)tl.out_row_b * (batch - 1) + d.M; }
       else ok = false;
     }
     if (ok) {
