@@ -153,7 +153,7 @@ def workload_config(args, n):
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
-    from ldm_image_generator_b200 import DDPM, Decoder, UNet
+    from ldm_image_generator_b200 import DDPM, Decoder, UNet, parallel
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -168,25 +168,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     B, L = args.batch, args.latent
     shape = (B, 8, L, L)
     # identical seeds on every rank; each rank takes its slice of the full noise batch
-    g = torch.Generator().manual_seed(0)
-    x_full = torch.randn(B * world, 8, L, L, generator=g)
-    x_host = x_full[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    x_host = parallel.shard_noise((B * world, 8, L, L), seed=0, rank=rank, world=world).pin_memory()
     x_dev = x_host.to(dev)
     out_host = torch.empty(B, 8 * L, 8 * L, 3, dtype=torch.uint8).pin_memory()
-    gathered = torch.empty(B * world, 8 * L, 8 * L, 3, dtype=torch.uint8, device=dev) if world > 1 else None
 
     def step_device():
-        random.seed(0)       # same expert plan on every rank and every step (fixed workload)
+        parallel.seed_plan_rng(0)       # same expert plan on every rank and every step (fixed workload)
         z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=x_dev, progress=False)
         return dec.decode_to_uint8(z)
 
     def step_e2e():
-        random.seed(0)
+        parallel.seed_plan_rng(0)
         xd = x_host.to(dev, non_blocking=True)
         z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=xd, progress=False)
         u8 = dec.decode_to_uint8(z)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, u8)
+            parallel.gather_images(u8, B * world)      # the one collective of the path: final image gather over NVLink
         out_host.copy_(u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the caller holds the images when the step returns
         return out_host
