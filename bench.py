@@ -139,6 +139,7 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": v, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    args._emit_ready()
     print(json.dumps(line), flush=True)
 
 
@@ -272,7 +273,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                 "sample": f"{len(vals)} x (1 UNet forward at batch 4 + 1 decode of 1 image), fp32 oracle port with the "
                                           f"Encodings MLP evaluated once per batch, extrapolated to {args.num_steps} steps/image "
                                           f"(UNet {vals[-1][1]:.3f} s, decode {vals[-1][2]:.3f} s)"}
+    args._emit_ready()
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
@@ -293,11 +296,22 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    args._emit_ready = lambda: None
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to stdout) go to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit_ready():
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    args._emit_ready = emit_ready
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run
+        emit_ready()
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
