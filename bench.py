@@ -231,7 +231,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     total_ms = sum(c["ms"] for c in classes.values()) or 1.0
     kernels = {}
     for name, c in classes.items():
-        tensor = name in ("gemm_tcgen05", "conv3x3_tcgen05", "gemm_cuda_core")
+        tensor = name in unet._handle.TENSOR_CLASSES
         ach = c["work"] / (c["ms"] * 1e-3) / (1e12 if tensor else 1e9) if c["ms"] > 0 and c["work"] > 0 else None
         kernels[name] = {"share": round(c["ms"] / total_ms, 4), "ms": c["ms"], "launches": c["launches"],
                          "achieved": None if ach is None else round(ach, 2), "unit": "TFLOP/s" if tensor else "GB/s"}

@@ -115,11 +115,17 @@ int ldmb_debug_tc_trace(ldmb_handle* h, int enable, int64_t* stamps_host, int ma
 /* Per-kernel-class device timing for roofline reports (bench.py).  Between begin and end every launch is
  * bracketed by CUDA events on its stream; end synchronises and returns, per class, the summed event time (ms),
  * the summed algorithmic work (FLOPs for the GEMM/conv classes, bytes for the HBM-bound ones) and the launch count.
- * Classes: 0 tcgen05 GEMM, 1 tcgen05 3x3 conv, 2 CUDA-core GEMM/conv, 3 ChannelNorm+FiLM, 4 window attention, 5 other.
+ * Classes (tcgen05 unless noted): 0 ReGLU a|b GEMM, 1 ReGLU c (+ attention out_proj) GEMM into the residual stream,
+ * 2 attention in_proj GEMM, 3 hoisted Encodings MLP GEMMs, 4 level-change 1x1 convs, 5 grouped 3x3 conv,
+ * 6 VAE dense 3x3 conv, 7 VAE ConvTranspose / 1x1 GEMMs, 8 CUDA-core GEMM/conv (fp32 validation mode, toy widths),
+ * 9 ChannelNorm+FiLM, 10 window attention core, 11 stem + final (decoder_last + DDIM update), 12 other.
  * Arrays must hold LDMB_PROFILE_CLASSES entries. */
-#define LDMB_PROFILE_CLASSES 6
+#define LDMB_PROFILE_CLASSES 13
 int ldmb_profile_begin(ldmb_handle* h);
 int ldmb_profile_end(ldmb_handle* h, double* ms, double* work, int64_t* launches);
+/* Debug (tools/ablate.py): launches of the classes in `mask` (bit k = class k) are skipped -- results are garbage,
+ * but timing a step with and without a class gives that class's cost inside the CUDA-graph replay. */
+int ldmb_debug_skip_classes(ldmb_handle* h, uint32_t mask);
 
 /* ---------------------------------------------------------------- UNet (unet.py) */
 int ldmb_unet_configure(ldmb_handle* h, const ldmb_unet_config* cfg);
@@ -181,6 +187,13 @@ int ldmb_conv3x3(ldmb_handle* h, const void* in, const void* W, const float* bia
 /* ChannelNorm + FiLM (modules.py:23-25, unet.py:22): x fp32 [M,C], film fp32 [HW, 2C] -> out [M,C] in handle precision. */
 int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float* film, void* out, int M, int C, int HW,
                           void* stream);
+
+/* Window attention core (attention.py:13-85 + torch MHA, after in_proj and before out_proj): qkv [B*H*W, 3C] and
+ * xm [B*H*W, C] in the handle's precision, b_in fp32 [3C] (in_proj bias: the q/k/v of zero-padded tokens),
+ * att [B*H*W, ldo>=C].  window win_h x win_w, shift 0 (bool pad mask) or != 0 (rolled window, float key bias =
+ * channel 0 of the rolled xm).  force_simt: the CUDA-core kernel instead of the mma.sync one in bf16 mode. */
+int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const float* b_in, void* att, int64_t ldo,
+                          int B, int H, int W, int C, int win_h, int win_w, int shift, int force_simt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,12 @@ cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W
 // key bias from xm(T) channel 0 when shift != 0, writes att(T) rows of stride ldo
 cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
                                     bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
-                                    int shift, const int* skip, cudaStream_t st);
+                                    int shift, const int* skip, cudaStream_t st, bool force_simt = false);
+// bf16 tensor-path (mma.sync) implementation of the same contract, 4 heads per CTA (kernels_attn.cu)
+bool window_attention_mma_supported(int C, int head_dim, int win_h, int win_w, long long ldo);
+cudaError_t launch_window_attention_mma(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo, int B,
+                                        int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
+                                        cudaStream_t st);
 // decoder_last ConvTranspose (unet.py:78,102) fused with the DDIM update (ddpm.py:81-91).
 // x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; x_in/out/noise NCHW fp32 [B,Cin,H*s,W*s]; ddim_enabled 0 = eps only.
 // sp (device): x_in / out / noise pointers and the DDIM scalars of this step.

@@ -1,0 +1,220 @@
+// Window attention core on the warp-level tensor path (bf16 mma.sync m16n8k16, fp32 softmax), sm_100a.
+//
+// attention.py:13-85 + torch MHA as called there: per (image, window, head) S = (q/sqrt(32)) k^T + key bias,
+// softmax over the keys, O = P v.  L = window tokens (36 for the 6x6 windows, 16 for the global 4x4 case) and
+// d = 32, so one (window, head) problem is 2 x 36x36x32 MACs: far too small for a tcgen05 tile (M = 128), and
+// at 0.3 % of the step's FLOPs the kernel is bound by moving qkv (3 M C bf16 in, M C bf16 out), not by math.
+// One CTA = one (image, window) x 4 heads, one warp per head:
+//   * q/k/v rows of the window are gathered with 16-byte loads into padded shared memory (index arithmetic
+//     replaces the reference's pad / roll / split / concat copies, see window_attention_kernel in kernels_simt.cu)
+//   * S: ldmatrix A (q) / B (k) fragments, MT x 2MT x 2 mma; scale, key bias (-inf mask or float bias), row softmax
+//     with quad shuffles; P stays in registers and is re-used as the A fragment of the second product
+//   * O: ldmatrix.trans B (v) fragments, MT x 4 x MT mma; normalised, staged through shared memory and written
+//     with 16-byte coalesced stores (pad tokens are cropped, attention.py:56).
+#include "kernels.h"
+
+#include <math.h>
+
+namespace {
+
+constexpr int kD = 32;          // head_dim (unet.py:26)
+constexpr int kHC = 4;          // heads per CTA = warps per CTA
+constexpr int kRow = kHC * kD;  // channels per CTA
+constexpr int kLd = kRow + 8;   // padded smem row (bf16 elements): 272 B, conflict-free for ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// MT = ceil(L / 16) query/key tiles of 16 (L <= 16 * MT)
+template <int MT>
+__global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
+    const bf16* __restrict__ qkv, const bf16* __restrict__ xm, const float* __restrict__ b_in, bf16* __restrict__ att,
+    long long ldo, int H, int W, int C, int wh, int ww, int shift, int Hp, int Wp, const int* __restrict__ skip) {
+  pdl_wait();
+  if (skip != nullptr && *skip != 0) return;
+  constexpr int LP = 16 * MT, NT = 2 * MT;
+  __shared__ __align__(16) bf16 Qs[LP * kLd];
+  __shared__ __align__(16) bf16 Ks[LP * kLd];
+  __shared__ __align__(16) bf16 Vs[LP * kLd];
+  __shared__ float kb[LP];
+  __shared__ long long rowm[LP];
+  const int L = wh * ww;
+  const int nww = Wp / ww, nwin = (Hp / wh) * nww;
+  const int b = blockIdx.x / nwin, win = blockIdx.x % nwin;
+  const int wi = win / nww, wj = win % nww;
+  const int ch0 = blockIdx.y * kRow;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < LP) {
+    long long rm = -2;          // -2: tile padding (no token), -1: window slot outside the image (pad token)
+    float bias = -INFINITY;
+    if (tid < L) {
+      const int si = tid / ww, sj = tid % ww;
+      const int pi = (wi * wh + si - shift + Hp) % Hp, pj = (wj * ww + sj - shift + Wp) % Wp;
+      const bool pad = pi >= H || pj >= W;
+      rm = pad ? -1 : ((long long)b * H + pi) * W + pj;
+      if (shift == 0) {
+        bias = pad ? -INFINITY : 0.f;                       // bool key_padding_mask (attention.py:27-35)
+      } else {                                              // float "mask" = rolled activation, channel 0 (attention.py:40)
+        const int qi = (pi - shift + Hp) % Hp, qj = (pj - shift + Wp) % Wp;
+        bias = (qi < H && qj < W) ? __bfloat162float(xm[(((long long)b * H + qi) * W + qj) * C]) : 0.f;
+      }
+    }
+    rowm[tid] = rm;
+    kb[tid] = bias;
+  }
+  __syncthreads();
+  // ---- gather q | k | v rows of this (window, head chunk): 16 x 16-byte pieces per token per matrix
+  for (int idx = tid; idx < LP * 3 * (kRow / 8); idx += 32 * kHC) {
+    const int piece = idx % (kRow / 8), which = (idx / (kRow / 8)) % 3, tok = idx / (3 * (kRow / 8));
+    const long long m = rowm[tok];
+    bf16* dst = (which == 0 ? Qs : (which == 1 ? Ks : Vs)) + tok * kLd + piece * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (m >= 0) {
+      v = __ldg(reinterpret_cast<const uint4*>(qkv + m * 3 * C + (long long)which * C + ch0 + piece * 8));
+    } else if (m == -1 && which != 0) {                     // pad token: x = 0 -> k, v = in_proj bias (attention.py:19-23)
+      const float* bp = b_in + which * C + ch0 + piece * 8;
+      v.x = pack2(bp[0], bp[1]); v.y = pack2(bp[2], bp[3]); v.z = pack2(bp[4], bp[5]); v.w = pack2(bp[6], bp[7]);
+    }
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int hc = warp * kD;                                 // this warp's head: columns [hc, hc + 32)
+  // ---- S = q k^T
+  uint32_t qa[MT][2][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = hc + ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Qs + row * kLd + col)), qa[mt][ks][0], qa[mt][ks][1], qa[mt][ks][2],
+              qa[mt][ks][3]);
+    }
+  float s[MT][NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    uint32_t kf[4];
+    {
+      const int row = nt * 8 + (lane & 7), col = hc + (lane >> 3) * 8;
+      ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Ks + row * kLd + col)), kf[0], kf[1], kf[2], kf[3]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+      mma_bf16(s[mt][nt], qa[mt][0][0], qa[mt][0][1], qa[mt][0][2], qa[mt][0][3], kf[0], kf[1]);
+      mma_bf16(s[mt][nt], qa[mt][1][0], qa[mt][1][1], qa[mt][1][2], qa[mt][1][3], kf[2], kf[3]);
+    }
+  }
+  // ---- softmax over keys (rows g and g+8 of every 16-row tile; a row is spread over the 4 lanes of a quad)
+  const float scale_l2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
+  float inv[MT][2];
+  uint32_t pa[MT][MT][4];                                    // P as A fragments of the second product
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float b0 = kb[nt * 8 + 2 * t4] * 1.4426950408889634f, b1 = kb[nt * 8 + 2 * t4 + 1] * 1.4426950408889634f;
+      s[mt][nt][0] = fmaf(s[mt][nt][0], scale_l2, b0); s[mt][nt][1] = fmaf(s[mt][nt][1], scale_l2, b1);
+      s[mt][nt][2] = fmaf(s[mt][nt][2], scale_l2, b0); s[mt][nt][3] = fmaf(s[mt][nt][3], scale_l2, b1);
+      mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[mt][nt][0] = exp2f(s[mt][nt][0] - mx0); s[mt][nt][1] = exp2f(s[mt][nt][1] - mx0);
+      s[mt][nt][2] = exp2f(s[mt][nt][2] - mx1); s[mt][nt][3] = exp2f(s[mt][nt][3] - mx1);
+      sum0 += s[mt][nt][0] + s[mt][nt][1];
+      sum1 += s[mt][nt][2] + s[mt][nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    inv[mt][0] = 1.f / sum0; inv[mt][1] = 1.f / sum1;
+#pragma unroll
+    for (int kt = 0; kt < MT; ++kt) {
+      pa[mt][kt][0] = pack2(s[mt][2 * kt][0], s[mt][2 * kt][1]);
+      pa[mt][kt][1] = pack2(s[mt][2 * kt][2], s[mt][2 * kt][3]);
+      pa[mt][kt][2] = pack2(s[mt][2 * kt + 1][0], s[mt][2 * kt + 1][1]);
+      pa[mt][kt][3] = pack2(s[mt][2 * kt + 1][2], s[mt][2 * kt + 1][3]);
+    }
+  }
+  // ---- O = P v
+  float o[MT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) o[mt][dt][0] = o[mt][dt][1] = o[mt][dt][2] = o[mt][dt][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < MT; ++kt)
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {                         // pairs of 8-wide d tiles
+      uint32_t vf[4];
+      const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = hc + (dp * 2 + (lane >> 4)) * 8;
+      ldsm_x4_t(static_cast<uint32_t>(__cvta_generic_to_shared(Vs + row * kLd + col)), vf[0], vf[1], vf[2], vf[3]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        mma_bf16(o[mt][dp * 2], pa[mt][kt][0], pa[mt][kt][1], pa[mt][kt][2], pa[mt][kt][3], vf[0], vf[1]);
+        mma_bf16(o[mt][dp * 2 + 1], pa[mt][kt][0], pa[mt][kt][1], pa[mt][kt][2], pa[mt][kt][3], vf[2], vf[3]);
+      }
+    }
+  // ---- stage this head's output over its own (consumed) q columns, then coalesced row stores
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      bf16* p0 = Qs + (mt * 16 + g) * kLd + hc + dt * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(p0) = pack2(o[mt][dt][0] * inv[mt][0], o[mt][dt][1] * inv[mt][0]);
+      *reinterpret_cast<uint32_t*>(p0 + 8 * kLd) = pack2(o[mt][dt][2] * inv[mt][1], o[mt][dt][3] * inv[mt][1]);
+    }
+  __syncthreads();
+  for (int idx = tid; idx < L * (kRow / 8); idx += 32 * kHC) {
+    const int piece = idx % (kRow / 8), tok = idx / (kRow / 8);
+    const long long m = rowm[tok];
+    if (m < 0) continue;                                    // outputs at pad positions are cropped (attention.py:56)
+    *reinterpret_cast<uint4*>(att + m * ldo + ch0 + piece * 8) = *reinterpret_cast<const uint4*>(Qs + tok * kLd + piece * 8);
+  }
+}
+
+}  // namespace
+
+bool window_attention_mma_supported(int C, int head_dim, int win_h, int win_w, long long ldo) {
+  return head_dim == kD && (C / kD) % kHC == 0 && C % kRow == 0 && win_h * win_w <= 48 && ldo % 8 == 0 && C % 8 == 0;
+}
+
+cudaError_t launch_window_attention_mma(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo, int B,
+                                        int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
+                                        cudaStream_t st) {
+  const int Hp = (H + win_h - 1) / win_h * win_h, Wp = (W + win_w - 1) / win_w * win_w;
+  const int L = win_h * win_w;
+  dim3 grid(B * (Hp / win_h) * (Wp / win_w), C / kRow);
+  if (grid.y > 65535u) return cudaErrorNotSupported;
+  const bf16* q = static_cast<const bf16*>(qkv);
+  const bf16* x = static_cast<const bf16*>(xm);
+  bf16* o = static_cast<bf16*>(att);
+  if (L <= 16) launch_k((window_attention_mma_kernel<1>), grid, 32 * kHC, 0, st, q, x, b_in, o, ldo, H, W, C, win_h, win_w, shift, Hp, Wp, skip);
+  else if (L <= 32) launch_k((window_attention_mma_kernel<2>), grid, 32 * kHC, 0, st, q, x, b_in, o, ldo, H, W, C, win_h, win_w, shift, Hp, Wp, skip);
+  else launch_k((window_attention_mma_kernel<3>), grid, 32 * kHC, 0, st, q, x, b_in, o, ldo, H, W, C, win_h, win_w, shift, Hp, Wp, skip);
+  return cudaGetLastError();
+}

@@ -186,8 +186,9 @@ template <> struct Pack4<bf16> {
   }
 };
 
-// ROWS rows per warp are in flight at once (independent loads) so that narrow rows (C = 128: one float4 per lane)
-// still keep enough bytes in flight to cover HBM latency.
+// One warp normalises the same pixel p of ROWS consecutive images: the FiLM row (mul | bias, fp32, 8C bytes -- twice
+// the bytes of the x row itself) depends on (t, p) only, so it is loaded once and re-used for the ROWS images when
+// they share a timestep (always, in DDPM.sample).  The ROWS x rows are independent 16-byte loads in flight.
 template <typename T, int MAXV, int ROWS>
 __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict__ x, const float* __restrict__ film,
                                                         const int* __restrict__ t_index, T* __restrict__ out,
@@ -196,28 +197,45 @@ __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict_
   if (skip != nullptr && *skip != 0) return;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; mb < M; mb += warps_per_grid * ROWS) {
+  const int B = M / HW;
+  const int groups = (B + ROWS - 1) / ROWS;
+  const float inv_c = 1.f / (float)C, inv_c1 = 1.f / (float)(C - 1);
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < groups * HW; item += warps_per_grid) {
+    const int p = item % HW, b0 = (item / HW) * ROWS;
     float4 v[ROWS][MAXV];
     float sum[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       sum[r] = 0.f;
-      const int m = mb + r;
-      const float* xr = x + (long long)m * C;
+      const float* xr = x + ((long long)(b0 + r) * HW + p) * C;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = i * 128 + lane * 4;
-        if (m < M && c < C) {
+        if (b0 + r < B && c < C) {
           v[r][i] = __ldg(reinterpret_cast<const float4*>(xr + c));
           sum[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
         }
       }
     }
+    float4 mu[MAXV], bi[MAXV];
+    int t_cur = -1;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int m = mb + r;
-      if (m >= M) break;                               // warp-uniform
-      const float mean = warp_sum(sum[r]) / (float)C;
+      if (b0 + r >= B) break;                          // warp-uniform
+      const int ti = t_index ? t_index[b0 + r] : 0;
+      if (ti != t_cur) {                               // warp-uniform
+        t_cur = ti;
+        const float* fr = film + ((long long)ti * HW + p) * 2 * C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int c = i * 128 + lane * 4;
+          if (c < C) {
+            mu[i] = __ldg(reinterpret_cast<const float4*>(fr + c));
+            bi[i] = __ldg(reinterpret_cast<const float4*>(fr + C + c));
+          }
+        }
+      }
+      const float mean = warp_sum(sum[r]) * inv_c;
       float sq = 0.f;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
@@ -227,19 +245,14 @@ __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict_
           sq += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
         }
       }
-      const float sd = sqrtf(warp_sum(sq) / (float)(C - 1) + eps);   // unbiased variance (modules.py:24)
-      const int trow = (t_index ? t_index[m / HW] : 0) * HW + m % HW;
-      const float* fr = film + (long long)trow * 2 * C;
-      T* orow = out + (long long)m * C;
+      const float rs = 1.f / sqrtf(warp_sum(sq) * inv_c1 + eps);   // unbiased variance (modules.py:24)
+      T* orow = out + ((long long)(b0 + r) * HW + p) * C;
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = i * 128 + lane * 4;
-        if (c < C) {
-          const float4 mu = __ldg(reinterpret_cast<const float4*>(fr + c));
-          const float4 bi = __ldg(reinterpret_cast<const float4*>(fr + C + c));
-          Pack4<T>::store(orow + c, (v[r][i].x / sd) * mu.x + bi.x, (v[r][i].y / sd) * mu.y + bi.y,
-                          (v[r][i].z / sd) * mu.z + bi.z, (v[r][i].w / sd) * mu.w + bi.w);
-        }
+        if (c < C)
+          Pack4<T>::store(orow + c, fmaf(v[r][i].x * rs, mu[i].x, bi[i].x), fmaf(v[r][i].y * rs, mu[i].y, bi[i].y),
+                          fmaf(v[r][i].z * rs, mu[i].z, bi[i].z), fmaf(v[r][i].w * rs, mu[i].w, bi[i].w));
       }
     }
   }
@@ -443,9 +456,9 @@ __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restri
   if (sp != nullptr) x = sp->x_in;
   const int J = Cin * s * s;
   float* xs = smem_in;                    // [kPixIn][J + 1]
-  float* ws = smem_in + kPixIn * (J + 1); // [Cout][J]
+  float* ws = smem_in + kPixIn * (J + 1); // [J][Cout]  (transposed: consecutive threads read consecutive channels)
   const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * kPixIn;
-  for (int i = threadIdx.x; i < Cout * J; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout * J; i += blockDim.x) ws[(i % J) * Cout + i / J] = w[i];
   for (int i = threadIdx.x; i < kPixIn * J; i += blockDim.x) {
     const int p = i % kPixIn, j = i / kPixIn;           // consecutive threads -> consecutive pixels (contiguous along w)
     const long long m = m0 + p;
@@ -458,14 +471,30 @@ __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restri
     xs[p * (J + 1) + j] = v;
   }
   __syncthreads();
+  if ((Cout & 3) == 0) {
+    const int q = Cout >> 2;                             // channel quads per pixel
+    for (int i = threadIdx.x; i < kPixIn * q; i += blockDim.x) {
+      const int p = i / q, co = (i % q) * 4;
+      const long long m = m0 + p;
+      if (m >= M) break;
+      float4 acc = *reinterpret_cast<const float4*>(bias + co);
+      const float* xr = xs + p * (J + 1);
+      for (int j = 0; j < J; ++j) {
+        const float xv = xr[j];
+        const float4 wv = *reinterpret_cast<const float4*>(ws + j * Cout + co);
+        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+      }
+      Pack4<TO>::store(out + m * Cout + co, acc.x, acc.y, acc.z, acc.w);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < kPixIn * Cout; i += blockDim.x) {
     const int p = i / Cout, co = i % Cout;
     const long long m = m0 + p;
     if (m >= M) break;
     float acc = bias[co];
     const float* xr = xs + p * (J + 1);
-    const float* wr = ws + co * J;
-    for (int j = 0; j < J; ++j) acc = fmaf(xr[j], wr[j], acc);
+    for (int j = 0; j < J; ++j) acc = fmaf(xr[j], ws[j * Cout + co], acc);
     out[m * Cout + co] = from_f<TO>(acc);
   }
 }
@@ -544,6 +573,78 @@ __global__ void __launch_bounds__(256) final_kernel(const float* __restrict__ x,
       }
     }
     out[o] = r;
+  }
+}
+
+// decoder_last + DDIM update, fast path for C0 = 128*V channels and J = Cin*s*s <= 8 outputs per pixel: one warp per
+// pixel (the row is one coalesced 16-byte load per lane), the lane's [J][4V] weight slice lives in registers, the 8
+// partial dot products are folded across the warp with 9 shuffles, and the 8 lanes that end up owning one output
+// each apply the DDIM update (ddpm.py:81-91) and write NCHW.  Bytes: 4*C0 per pixel in, 12*J in/out.
+template <int V>
+__global__ void __launch_bounds__(256) final_warp_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const StepParams* __restrict__ sp,
+                                                         int B, int Cin, int H, int W, int s, int C0) {
+  pdl_wait();
+  const StepParams co = *sp;
+  const float* __restrict__ xin = co.x_in;
+  const float* __restrict__ noise = co.noise;
+  float* __restrict__ out = co.out;
+  const int lane = threadIdx.x & 31;
+  const int J = Cin * s * s;
+  float wr[8][4 * V];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wr[j][4 * i + e] = j < J ? w[(long long)(i * 128 + lane * 4 + e) * J + j] : 0.f;
+  // output owned by this lane after the fold: bit 4 -> +4, bit 3 -> +2, bit 2 -> +1
+  const int jl = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const float bj = jl < J ? bias[jl / (s * s)] : 0.f;
+  const long long M = (long long)B * H * W;
+  const long long wpg = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += wpg) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + m * C0 + i * 128 + lane * 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        a[j] = fmaf(v.x, wr[j][4 * i], fmaf(v.y, wr[j][4 * i + 1], fmaf(v.z, wr[j][4 * i + 2], fmaf(v.w, wr[j][4 * i + 3], a[j]))));
+    }
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 16); a[i] = (hi ? a[i + 4] : a[i]) + r; }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 2], 8); a[i] = (hi ? a[i + 2] : a[i]) + r; }
+    }
+    {
+      const bool hi = lane & 4;
+      const float r = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[1], 4);
+      a[0] = (hi ? a[1] : a[0]) + r;
+    }
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    if ((lane & 3) == 0 && jl < J) {
+      const int ci = jl / (s * s), dy = (jl / s) % s, dx = jl % s;
+      const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+      const long long o = (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
+      const float eps = a[0] + bj;
+      float r = eps;
+      if (co.ddim_enabled) {
+        const float x0 = (xin[o] - co.c_eps_in * eps) / co.c_div;
+        if (co.final_step) r = x0;
+        else {
+          r = co.c_x0 * x0 + co.c_eps_out * eps;
+          r += co.sigma * (noise ? noise[o] : 0.f);
+        }
+      }
+      out[o] = r;
+    }
   }
 }
 
@@ -634,14 +735,22 @@ cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float
   return cudaGetLastError();
 }
 
+template <typename T, int MAXV, int ROWS>
+static void norm_film_launch(const float* x, const float* film, const int* t_index, T* out, int M, int C, int HW, float eps,
+                             const int* skip, cudaStream_t st) {
+  const long long items = (long long)((M / HW + ROWS - 1) / ROWS) * HW;     // warps of work
+  launch_k((norm_film_kernel<T, MAXV, ROWS>), grid_for(items * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+}
+
 template <typename T>
 static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
                                       int HW, float eps, const int* skip, cudaStream_t st) {
-  if (C <= 128) launch_k((norm_film_kernel<T, 1, 4>), grid_for((long long)((M + 3) / 4) * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 256) launch_k((norm_film_kernel<T, 2, 2>), grid_for((long long)((M + 1) / 2) * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 512) launch_k((norm_film_kernel<T, 4, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 1024) launch_k((norm_film_kernel<T, 8, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
-  else if (C <= 2048) launch_k((norm_film_kernel<T, 16, 1>), grid_for((long long)M * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, C, HW, eps, skip);
+  if (M % HW != 0) return cudaErrorInvalidValue;
+  if (C <= 128) norm_film_launch<T, 1, 4>(x, film, t_index, out, M, C, HW, eps, skip, st);
+  else if (C <= 256) norm_film_launch<T, 2, 4>(x, film, t_index, out, M, C, HW, eps, skip, st);
+  else if (C <= 512) norm_film_launch<T, 4, 2>(x, film, t_index, out, M, C, HW, eps, skip, st);
+  else if (C <= 1024) norm_film_launch<T, 8, 1>(x, film, t_index, out, M, C, HW, eps, skip, st);
+  else if (C <= 2048) norm_film_launch<T, 16, 1>(x, film, t_index, out, M, C, HW, eps, skip, st);
   else return cudaErrorNotSupported;
   return cudaGetLastError();
 }
@@ -704,9 +813,11 @@ static cudaError_t window_attention_launch(const void* qkv, const void* xm, cons
 
 cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
                                     bool is_bf16, int B, int H, int W, int C, int head_dim, int win_h, int win_w,
-                                    int shift, const int* skip, cudaStream_t st) {
+                                    int shift, const int* skip, cudaStream_t st, bool force_simt) {
   if (head_dim != 32 || win_h * win_w > 64 || C % 32) return cudaErrorNotSupported;
   const int heads = C / 32;
+  if (is_bf16 && !force_simt && window_attention_mma_supported(C, head_dim, win_h, win_w, ldo))
+    return launch_window_attention_mma(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
   if (is_bf16) {
     if (heads % 4 == 0) return window_attention_launch<bf16, 4>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
     if (heads % 2 == 0) return window_attention_launch<bf16, 2>(qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, skip, st);
@@ -720,6 +831,12 @@ cudaError_t launch_final(const float* x, const float* w, const float* bias, cons
                          int W, int s, int C0, cudaStream_t st) {
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
+  if (Cin * s * s <= 8 && (C0 == 128 || C0 == 256)) {
+    const int grid = grid_for(M * 32, 256, 148 * 4);
+    if (C0 == 128) launch_k((final_warp_kernel<1>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
+    else launch_k((final_warp_kernel<2>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
+    return cudaGetLastError();
+  }
   launch_k((final_kernel), (unsigned)((M + 31) / 32), 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
   return cudaGetLastError();
 }

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <initializer_list>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -45,6 +47,7 @@ struct TcTiling {
   int m_tiles, n_tiles, num_kb, total;
   int TW, TH, TB;   // AM_CONV3: the 128-pixel tile is TB images x TH rows x TW columns
   int tma_out;      // epilogue goes through smem + TMA store / reduce
+  int splits, kb_per;   // split-K (EPI_ACCUM_F32 through TMA reduce-add only): tile t covers k-blocks [sp*kb_per, ...)
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
 };
 
@@ -134,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_z = tl.m_tiles * tl.n_tiles;
+  const int tiles_per_split = tl.total / tl.splits;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail.
   if (threadIdx.x == 0) trace_stamp(trace, 1);                 // setup done
   pdl_wait();
@@ -153,9 +157,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
-        const int z = t / tiles_per_z, rem = t % tiles_per_z;
+        const int sp = t / tiles_per_split, ts = t % tiles_per_split;
+        const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
         const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
         const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
+        const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
         int b0 = 0, h0 = 0, w0 = 0;
         if (AMODE == AM_CONV3) {
           const int hw = d.cH * d.cW;
@@ -164,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           h0 = r / d.cW;
           w0 = r % d.cW;
         }
-        for (int kb = 0; kb < tl.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
@@ -185,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           brow += (int)(z * d.w_row_b) + (int)rank * Cfg::B_ROWS;      // this CTA's share of the tile's weight rows
           if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
           else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
-          if (t == (int)(blockIdx.x / CG) && kb == 0) trace_stamp(trace, 3);   // first loads issued
+          if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 3);   // first loads issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -200,18 +206,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < tl.num_kb; ++kb) {
+        const int kb0 = (t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           wait_bar(&full[stage], phase, s_abort, fault, 3);
-          if (t == (int)(blockIdx.x / CG) && kb == 0) trace_stamp(trace, 4);   // first operands landed
+          if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (CG == 2) ptx::umma_f16_2sm(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
-                                           (kb | k) != 0 ? 1u : 0u);
+                                           (kb != kb0 || k != 0) ? 1u : 0u);
             else ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
-                               (kb | k) != 0 ? 1u : 0u);
+                               (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]);
@@ -236,14 +243,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
     for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
-      const int z = t / tiles_per_z, rem = t % tiles_per_z;
+      const int sp = t / tiles_per_split, ts = t % tiles_per_split;
+      const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
         float bv = 0.f;
-        if (n < d.N && d.bias != nullptr) {
+        if (n < d.N && d.bias != nullptr && sp == 0) {      // split-K: the bias rides with the first K slice
           const float* bp = d.bias + z * d.bias_off_b;
           if (d.sel == 2) { for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; }
           else if (d.sel == 1) bv = bp[srow(n / d.sel_span) + n % d.sel_span];
@@ -497,7 +505,15 @@ int pick_bn(const GemmDesc& d, int num_sms) {
     if (d.epi == EPI_REGLU && bn < 128) return false;
     return true;
   };
-  (void)m_tiles; (void)batch; (void)num_sms;
+  // Few-row GEMMs (the hoisted Encodings MLP, the level-change 1x1 convs: M <= 128) stream their weights once
+  // from HBM: what matters is enough CTAs to pull the full HBM bandwidth, so take the widest tile that still gives
+  // every SM a CTA (else the narrowest).
+  if (m_tiles == 1 && d.sel == 0 && d.epi != EPI_REGLU) {
+    for (int bn : {256, 128, 64})
+      if (ok(bn) && (long long)((d.N + bn - 1) / bn) * batch >= num_sms) return bn;
+    for (int bn : {64, 128, 256}) if (ok(bn)) return bn;
+    return 0;
+  }
   if (ok(256)) return 256;       // the widest tile: L2->SM bytes per FLOP decide the main-loop rate
   if (ok(128)) return 128;
   if (ok(64)) return 64;
@@ -617,6 +633,7 @@ static cudaError_t launch_tc_bn(TcContext* ctx, int bn, const CUtensorMap& tmA, 
   return launch_tc_inst<64, AMODE, CG>(ctx, tmA, tmB, tmO, d, tl, s);
 }
 
+static int g_tc_splitk = getenv("LDMB_NO_SPLITK") ? 0 : 1;
 static int g_tc_force_cg = getenv("LDMB_TC_CG") ? atoi(getenv("LDMB_TC_CG")) : 0;   // debug: 1 or 2 forces the CTA-group size
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
@@ -631,6 +648,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   tl.n_tiles = (d.N + bn - 1) / bn;
   tl.num_kb = d.K / BK;
   tl.total = tl.m_tiles * tl.n_tiles * batch;
+  tl.splits = 1; tl.kb_per = tl.num_kb;
   tl.TW = tl.TH = tl.TB = 0;
 
   CUtensorMap tmA, tmB;
@@ -697,6 +715,18 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
       tl.tma_out = 1;
+    }
+  }
+  // split-K: an accumulate-into-the-residual GEMM with too few output tiles to fill the machine (deep UNet levels:
+  // M = 1024..4096 rows, K = 3C..4C) is cut along K; every slice reduce-adds its partial tile into x with TMA.
+  if (tl.tma_out && d.epi == EPI_ACCUM_F32 && g_tc_splitk) {
+    const int base = tl.total * cg;
+    int sp = ctx->num_sms / (base > 0 ? base : 1);
+    if (sp > tl.num_kb / 4) sp = tl.num_kb / 4;              // at least 4 k-blocks (K = 256) per slice
+    if (sp > 1) {
+      tl.kb_per = (tl.num_kb + sp - 1) / sp;
+      tl.splits = (tl.num_kb + tl.kb_per - 1) / tl.kb_per;
+      tl.total *= tl.splits;
     }
   }
   if (d.amode == AM_ROWS)

@@ -117,11 +117,14 @@ struct VaeState {
 
 }  // namespace
 
-enum { PK_GEMM_TC = 0, PK_CONV_TC = 1, PK_GEMM_SIMT = 2, PK_NORM = 3, PK_ATTN = 4, PK_OTHER = 5, PK_COUNT = 6 };
+enum { PK_FFN_AB = 0, PK_FFN_C = 1, PK_QKV = 2, PK_ENC = 3, PK_LEVEL = 4, PK_GCONV = 5, PK_VAE_CONV = 6, PK_VAE_GEMM = 7,
+       PK_GEMM_SIMT = 8, PK_NORM = 9, PK_ATTN = 10, PK_EDGE = 11, PK_OTHER = 12, PK_COUNT = 13 };
+static_assert(PK_COUNT == LDMB_PROFILE_CLASSES, "profile classes");
 struct ProfRec { int kind; double work; cudaEvent_t a, b; };
 
 struct ldmb_handle {
   bool prof_on = false;
+  uint32_t skip_mask = 0;      // debug: classes whose launches are dropped (ldmb_debug_skip_classes)
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
@@ -161,6 +164,7 @@ int fail(ldmb_handle* h, int code, const char* fmt, ...) {
 // A kernel launch on stream `st`: counted, and bracketed by events when profiling is on.
 #define CKLP(KIND_, WORK_, call)                                                                     \
   do {                                                                                             \
+    if (h->skip_mask & (1u << (KIND_))) break;                                                     \
     ProfRec pr__;                                                                                  \
     const bool p__ = h->prof_on;                                                                   \
     if (p__) { pr__.kind = (KIND_); pr__.work = (double)(WORK_); pr__.a = h->get_event(); pr__.b = h->get_event(); cudaEventRecord(pr__.a, st); } \
@@ -184,10 +188,10 @@ void release(DevBuf& b) {
   b.p = nullptr; b.bytes = 0;
 }
 
-int gemm(ldmb_handle* h, const GemmDesc& d, cudaStream_t st, bool force_simt = false) {
+int gemm(ldmb_handle* h, const GemmDesc& d, cudaStream_t st, int kind, bool force_simt = false) {
   const double flops = 2.0 * d.M * (double)d.N * d.K * (d.batch > 0 ? d.batch : 1);
   if (h->bf16() && !h->force_simt && !force_simt && tc_supported(d))
-    CKLP(d.amode == AM_CONV3 ? PK_CONV_TC : PK_GEMM_TC, flops, launch_gemm_tc(h->tc, d, st));
+    CKLP(kind, flops, launch_gemm_tc(h->tc, d, st));
   else CKLP(PK_GEMM_SIMT, flops, launch_gemm_simt(d, h->bf16(), st));
   return LDMB_OK;
 }
@@ -308,6 +312,12 @@ extern "C" int ldmb_profile_end(ldmb_handle* h, double* ms, double* work, int64_
   }
   h->prof.clear();
   h->ev_next = 0;
+  return LDMB_OK;
+}
+extern "C" int ldmb_debug_skip_classes(ldmb_handle* h, uint32_t mask) {
+  if (!h) return LDMB_ERR_INVALID;
+  h->skip_mask = mask;
+  h->unet.ws_epoch++;          // captured graphs hold the old launch set
   return LDMB_OK;
 }
 extern "C" int ldmb_check_device_fault(ldmb_handle* h, void* stream) {
@@ -620,14 +630,14 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = x; d.ldo = C;
     d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32; d.plan = pl;
     d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
-    if ((rc = gemm(h, d, st))) return rc;
+    if ((rc = gemm(h, d, st, PK_GCONV))) return rc;
   }
   const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE; d.plan = pl;
-    if ((rc = gemm(h, d, st))) return rc;
+    if ((rc = gemm(h, d, st, PK_QKV))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
     CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
          launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
@@ -639,13 +649,13 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_stride = 2 * C; d.plan = pl;
-    if ((rc = gemm(h, d, st))) return rc;
+    if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
     // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases      (unet.py:44,47: ffn and attention in one update)
     GemmDesc c = gd();
     c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
     c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32;
     c.sel = 2; c.sel_span = C; c.sel_stride = C; c.plan = pl;
-    if ((rc = gemm(h, c, st))) return rc;
+    if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
   return LDMB_OK;
 }
@@ -665,15 +675,15 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
     GemmDesc a = gd();
     a.A = L.emb.p; a.lda = 2 * C; a.W = L.w1; a.ldw = 2 * C; a.bias = L.b1; a.out = L.h1.p; a.ldo = (long long)L.nb * 4 * C;
     a.M = Mt; a.N = L.nb * 4 * C; a.K = 2 * C; a.epi = EPI_STORE; a.act = ACT_RELU;
-    if ((rc = gemm(h, a, st))) return rc;
+    if ((rc = gemm(h, a, st, PK_ENC))) return rc;
     GemmDesc b = gd();
     b.A = L.h1.p; b.lda = (long long)L.nb * 4 * C; b.W = L.w2; b.ldw = 4 * C; b.bias = L.b2; b.out = L.film.p; b.ldo = 2 * C;
     b.M = Mt; b.N = 2 * C; b.K = 4 * C; b.epi = EPI_STORE_F32;
     b.batch = L.nb; b.a_koff_b = 4 * C; b.w_row_b = 2 * C; b.out_off_b = (long long)Mt * 2 * C; b.bias_off_b = 2 * C;
-    if ((rc = gemm(h, b, st))) return rc;
+    if ((rc = gemm(h, b, st, PK_ENC))) return rc;
   }
   // ---- encoder_first (unet.py:90)
-  CKL(launch_stem(u.sp_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
+  CKLP(PK_EDGE, 0, launch_stem(u.sp_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
                   cfg.channels[0], st));
   // ---- encoder (unet.py:92-98)
   int bi = 0;
@@ -689,7 +699,7 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
       GemmDesc d = gd();
       d.A = u.pooled.p; d.lda = C; d.W = L.w_down; d.ldw = C; d.bias = L.b_down; d.out = u.levels[l + 1].xs.p; d.ldo = Cn;
       d.M = B * (Hl / 2) * (Wl / 2); d.N = Cn; d.K = C; d.epi = EPI_STORE_F32;
-      if ((rc = gemm(h, d, st))) return rc;
+      if ((rc = gemm(h, d, st, PK_LEVEL))) return rc;
     }
   }
   // ---- decoder (unet.py:99-101); the deepest level continues in place (skip = 0)
@@ -704,14 +714,14 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
       GemmDesc d = gd();
       d.A = u.pooled.p; d.lda = Cn; d.W = L.w_up; d.ldw = Cn; d.bias = L.b_up; d.out = u.ylow.p; d.ldo = C;
       d.M = (int)Mlow; d.N = C; d.K = Cn; d.epi = EPI_STORE_F32;
-      if ((rc = gemm(h, d, st))) return rc;
+      if ((rc = gemm(h, d, st, PK_LEVEL))) return rc;
       CKL(launch_upsample_add(static_cast<float*>(L.xs.p), static_cast<const float*>(u.ylow.p), B, Hl, Wl, C, st));
     }
     for (int b = 0; b < cfg.blocks[l]; ++b, ++bi)
       if ((rc = run_block(h, u.blocks[bi], bi, B, Hl, Wl, n_t, st))) return rc;
   }
   // ---- decoder_last (unet.py:102) + DDIM update (ddpm.py:81-91)
-  CKL(launch_final(static_cast<const float*>(u.levels[0].xs.p), u.w_last, u.b_last, u.sp_dev, B, cfg.input_channels, Hs, Ws, s,
+  CKLP(PK_EDGE, 0, launch_final(static_cast<const float*>(u.levels[0].xs.p), u.w_last, u.b_last, u.sp_dev, B, cfg.input_channels, Hs, Ws, s,
                    cfg.channels[0], st));
   return LDMB_OK;
 }
@@ -1002,9 +1012,9 @@ int res_block(ldmb_handle* h, const ResW& R, const void* x, void* tmp, void* out
   GemmDesc d = gd();
   d.A = x; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = C; d.W = R.w1; d.ldw = 9LL * C; d.bias = R.b1;
   d.out = tmp; d.ldo = C; d.M = B * Hl * Wl; d.N = C; d.K = 9 * C; d.epi = EPI_STORE; d.act = ACT_LEAKY;
-  if ((rc = gemm(h, d, st))) return rc;
+  if ((rc = gemm(h, d, st, PK_VAE_CONV))) return rc;
   d.A = tmp; d.W = R.w2; d.bias = R.b2; d.out = out; d.res = x; d.ldr = C;
-  return gemm(h, d, st);
+  return gemm(h, d, st, PK_VAE_CONV);
 }
 
 }  // namespace
@@ -1041,7 +1051,7 @@ extern "C" int ldmb_vae_decode(ldmb_handle* h, const float* z_dev, float* img_de
       GemmDesc d = gd();
       d.A = cur; d.lda = Cp; d.W = L.w_resample; d.ldw = Cp; d.bias = L.b_resample; d.out = t1; d.ldo = C;
       d.M = B * (Hl / 2) * (Wl / 2); d.N = 4 * C; d.K = Cp; d.epi = EPI_CONVT; d.ctH = Hl / 2; d.ctW = Wl / 2; d.ctC = C;
-      if ((rc = gemm(h, d, st))) return rc;
+      if ((rc = gemm(h, d, st, PK_VAE_GEMM))) return rc;
       std::swap(cur, t1);
     }
     for (const ResW& R : L.res) {
@@ -1089,7 +1099,7 @@ extern "C" int ldmb_vae_encode(ldmb_handle* h, const float* img_dev, float* z_de
       GemmDesc d = gd();
       d.A = t1; d.lda = C; d.W = L.w_resample; d.ldw = C; d.bias = L.b_resample; d.out = t2; d.ldo = Cn;
       d.M = B * Hl * Wl; d.N = Cn; d.K = C; d.epi = EPI_STORE;
-      if ((rc = gemm(h, d, st))) return rc;
+      if ((rc = gemm(h, d, st, PK_VAE_GEMM))) return rc;
       std::swap(cur, t2);
     }
   }
@@ -1109,7 +1119,7 @@ extern "C" int ldmb_gemm(ldmb_handle* h, const void* A, const void* W, const flo
   d.A = A; d.lda = K; d.W = W; d.ldw = K; d.bias = bias; d.out = out; d.ldo = N; d.M = M; d.N = N; d.K = K;
   d.epi = out_f32 == 0 ? EPI_STORE : (out_f32 == 1 ? EPI_STORE_F32 : EPI_ACCUM_F32);
   d.act = act;
-  return gemm(h, d, static_cast<cudaStream_t>(stream), force_simt != 0);
+  return gemm(h, d, static_cast<cudaStream_t>(stream), PK_FFN_AB, force_simt != 0);
 }
 
 extern "C" int ldmb_conv3x3(ldmb_handle* h, const void* in, const void* W, const float* bias, void* out, int B, int H,
@@ -1119,7 +1129,7 @@ extern "C" int ldmb_conv3x3(ldmb_handle* h, const void* in, const void* W, const
   GemmDesc d = gd();
   d.A = in; d.lda = C; d.amode = AM_CONV3; d.cH = H; d.cW = Wd; d.cC = C; d.W = W; d.ldw = 9LL * C; d.bias = bias;
   d.out = out; d.ldo = N; d.M = B * H * Wd; d.N = N; d.K = 9 * C; d.epi = EPI_STORE; d.act = act;
-  return gemm(h, d, static_cast<cudaStream_t>(stream), force_simt != 0);
+  return gemm(h, d, static_cast<cudaStream_t>(stream), PK_VAE_CONV, force_simt != 0);
 }
 
 extern "C" int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float* film, void* out, int M, int C, int HW,
@@ -1128,5 +1138,17 @@ extern "C" int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()), launch_norm_film(x, film, nullptr, out, h->bf16(), M, C, HW, kNormEps, nullptr, st));
+  return LDMB_OK;
+}
+
+extern "C" int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const float* b_in, void* att, int64_t ldo,
+                                     int B, int H, int W, int C, int win_h, int win_w, int shift, int force_simt, void* stream) {
+  if (!h || !qkv || !xm || !b_in || !att || B < 1 || H < 1 || W < 1 || C < kHeadDim || win_h < 1 || win_w < 1 || ldo < C)
+    return LDMB_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKLP(PK_ATTN, (double)B * H * W * C * 4 * h->tsize(),
+       launch_window_attention(qkv, xm, b_in, att, ldo, h->bf16(), B, H, W, C, kHeadDim, win_h, win_w, shift, nullptr, st,
+                               force_simt != 0));
   return LDMB_OK;
 }

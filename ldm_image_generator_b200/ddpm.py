@@ -93,6 +93,7 @@ class DDPM(nn.Module):
         alpha_cum = torch.cumprod((1 - self.beta), dim=0)
         fused = isinstance(self.model, UNet)
         bar = tqdm(total=len(pairs), disable=not progress)
+        first = True
         for t, t_next in pairs:
             t, t_next = int(t), int(t_next)
             co, sigma = self.ddim_scalars(alpha_cum, t, t_next, eta)
@@ -100,7 +101,8 @@ class DDPM(nn.Module):
                 # ddpm.py:78 then :80 -- the noise is drawn every step (even for eta=0) so the torch
                 # generator stays in lock-step with the reference across un-reseeded calls
                 e = torch.randn(*x_shape, device=device)
-                x = self.model.denoise_step(x, t, co, e if co.sigma != 0.0 else None)
+                x = self.model.denoise_step(x, t, co, e if co.sigma != 0.0 else None, check_params=first)
+                first = False
             else:
                 # foreign eps-model: generic host-side update, same operation order as ddpm.py:82-91
                 e_theta = self.model(x=x, time=torch.full((x_shape[0],), t, device=device), condition=None)

@@ -94,7 +94,17 @@ class Handle:
     def device_fault(self) -> int:
         return int(self.lib.ldmb_check_device_fault(self.h, stream_ptr(self.device)))
 
-    PROFILE_CLASSES = ("gemm_tcgen05", "conv3x3_tcgen05", "gemm_cuda_core", "channelnorm_film", "window_attention", "other")
+    PROFILE_CLASSES = ("gemm_ffn_ab", "gemm_ffn_c", "gemm_qkv", "gemm_encodings", "gemm_level_change", "grouped_conv3x3",
+                       "vae_conv3x3", "vae_gemm", "gemm_cuda_core", "channelnorm_film", "window_attention", "stem_final", "other")
+    TENSOR_CLASSES = PROFILE_CLASSES[:9]
+
+    def skip_classes(self, names) -> None:
+        """Debug (tools/ablate.py): drop the launches of these classes (results become garbage)."""
+        mask = 0
+        for n in names:
+            mask |= 1 << self.PROFILE_CLASSES.index(n)
+        self.check(self.lib.ldmb_debug_skip_classes(self.h, mask))
+
 
     def profile_begin(self) -> None:
         self.check(self.lib.ldmb_profile_begin(self.h))
@@ -185,6 +195,11 @@ class Handle:
     def conv3x3(self, x, Wt, bias, out, B, H, W, Cc, N, act=0, force_simt=False) -> None:
         self.check(self.lib.ldmb_conv3x3(self.h, x.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
                                          out.data_ptr(), B, H, W, Cc, N, act, int(force_simt), stream_ptr(self.device)))
+
+    def window_attention(self, qkv, xm, b_in, att, B, H, W, Cc, win_h, win_w, shift, force_simt=False) -> None:
+        self.check(self.lib.ldmb_window_attention(self.h, qkv.data_ptr(), xm.data_ptr(), b_in.data_ptr(), att.data_ptr(),
+                                                  att.stride(-2), B, H, W, Cc, win_h, win_w, shift, int(force_simt),
+                                                  stream_ptr(self.device)))
 
     def channelnorm_film(self, x, film, out, M, Cc, HW) -> None:
         self.check(self.lib.ldmb_channelnorm_film(self.h, x.data_ptr(), film.data_ptr(), out.data_ptr(), M, Cc, HW,

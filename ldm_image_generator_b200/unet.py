@@ -120,16 +120,46 @@ class UNet(nn.Module):
             plan.append((0, e1, e2))
         return plan
 
-    def _prepare(self, device: torch.device) -> runtime.Handle:
+    def _prepare(self, device: torch.device, check_params: bool = True) -> runtime.Handle:
+        """The device handle, with every changed parameter re-uploaded.  Walking the 1 376-entry state_dict costs
+        milliseconds of host time, so DDPM.sample asks for it once per call (``check_params=False`` on the
+        remaining steps: weights cannot change inside the no_grad sampling loop)."""
         h = self._handle
         if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
             h = runtime.Handle(device, self.precision)
             h.unet_configure(self.input_channels, self.stage_blocks, self.stage_channels, self.stem_size)
             self._handle, self._pe_res = h, None
-        h.unet_load(self.state_dict(keep_vars=True).items())
+            check_params = True
+        if check_params:
+            items = self.__dict__.get("_param_items")
+            if items is None:      # (name, tensor) pairs; dropped whenever the module tree may have new tensors
+                items = self.__dict__["_param_items"] = list(self.state_dict(keep_vars=True).items())
+            h.unet_load(items)
         return h
 
-    def _run(self, x: torch.Tensor, t_values: Sequence[int], coef=None, noise=None, out=None, plan=None) -> torch.Tensor:
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float(): tensors may be replaced
+        self.__dict__.pop("_param_items", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):     # assign=True replaces the Parameter objects
+        self.__dict__.pop("_param_items", None)
+        return super().load_state_dict(*args, **kwargs)
+
+    def _time_tables(self, uniq: Sequence[int]):
+        """Per-level sinusoidal time tables (sinusoidal.py:31-41) of the distinct timesteps, cached per tuple."""
+        key = tuple(uniq)
+        cache = self.__dict__.setdefault("_te_cache", {})
+        te = cache.get(key)
+        if te is None:
+            if len(cache) >= 4096:
+                cache.clear()
+            tt = torch.tensor(list(uniq), dtype=torch.long)
+            te = [self.encoder_stages[lvl].stage.blocks[0].encodings.te.table(tt) for lvl in range(len(self.stage_channels))]
+            cache[key] = te
+        return te
+
+    def _run(self, x: torch.Tensor, t_values: Sequence[int], coef=None, noise=None, out=None, plan=None,
+             check_params: bool = True) -> torch.Tensor:
         runtime._require_cuda(x, "UNet input")
         p0 = next(self.parameters())
         runtime._require_cuda(p0, "UNet parameters")
@@ -138,7 +168,7 @@ class UNet(nn.Module):
                                f"but got {x.shape[1] if x.dim() == 4 else '?'} channels instead")
         x = runtime.f32c(x)
         with torch.cuda.device(x.device):
-            h = self._prepare(x.device)
+            h = self._prepare(x.device, check_params)
             B, _, H, W = x.shape
             Hs, Ws = H // self.stem_size, W // self.stem_size
             if self._pe_res != (Hs, Ws):
@@ -147,8 +177,7 @@ class UNet(nn.Module):
                 self._pe_res = (Hs, Ws)
             uniq = sorted(set(int(v) for v in t_values))
             index = {v: i for i, v in enumerate(uniq)}
-            tt = torch.tensor(uniq, dtype=torch.long)
-            te = [self.encoder_stages[lvl].stage.blocks[0].encodings.te.table(tt) for lvl in range(len(self.stage_channels))]
+            te = self._time_tables(uniq)
             if plan is None:
                 plan = self.draw_plan()
             if out is None:
@@ -166,7 +195,8 @@ class UNet(nn.Module):
         return self._run(x, t_values)
 
     def denoise_step(self, x: torch.Tensor, t: int, coef: "_lib.DdimCoef", noise: Optional[torch.Tensor] = None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, check_params: bool = True) -> torch.Tensor:
         """One iteration of DDPM.sample (ddpm.py:77-91): eps = UNet(x, t) and the DDIM update fused
         into the network's last kernel.  Writes into ``out`` (default: in place into ``x``)."""
-        return self._run(x, [int(t)] * x.shape[0], coef=coef, noise=noise, out=x if out is None else out)
+        return self._run(x, [int(t)] * x.shape[0], coef=coef, noise=noise, out=x if out is None else out,
+                         check_params=check_params)

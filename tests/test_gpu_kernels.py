@@ -112,3 +112,41 @@ def test_channelnorm_film(handles, C, prec):
     idx = torch.arange(M, device="cuda") % HW
     ref = xn * film[idx, :C] + film[idx, C:]
     assert _rel(out.float(), ref) < (4e-3 if prec == "bf16" else 2e-6)
+
+
+def _window_attention_torch(qkv, C, ws):
+    """Unpadded, unshifted windows: softmax(q k^T / sqrt(32)) v per (window, head), fp64."""
+    B, H, W, _ = qkv.shape
+    q, k, v = qkv.double().split(C, dim=-1)
+
+    def win(t):   # [B,H,W,C] -> [B, nh, nw, heads, ws*ws, 32]
+        t = t.reshape(B, H // ws, ws, W // ws, ws, C // 32, 32)
+        return t.permute(0, 1, 3, 5, 2, 4, 6).reshape(B, H // ws, W // ws, C // 32, ws * ws, 32)
+    s = torch.softmax(win(q) @ win(k).transpose(-1, -2) / 32 ** 0.5, dim=-1) @ win(v)
+    s = s.reshape(B, H // ws, W // ws, C // 32, ws, ws, 32).permute(0, 1, 4, 2, 5, 3, 6)
+    return s.reshape(B, H, W, C)
+
+
+@pytest.mark.parametrize("B,H,W,C,wh,ww,shift", [(2, 12, 12, 128, 6, 6, 0), (2, 12, 12, 128, 6, 6, 3), (3, 20, 28, 256, 6, 6, 0),
+                                                 (3, 20, 28, 256, 6, 6, 3), (5, 4, 4, 1024, 4, 4, 0), (2, 8, 8, 512, 6, 6, 3),
+                                                 (1, 32, 32, 128, 6, 6, 3), (2, 5, 3, 128, 5, 3, 0)])
+def test_window_attention_mma_kernel(handles, B, H, W, C, wh, ww, shift):
+    """bf16 mma.sync attention core vs the CUDA-core kernel (validated against the reference through the UNet
+    fixtures), including zero-padded windows, the rolled float key bias and the global small-image case."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + H * 17 + C + shift)
+    qkv = torch.randn(B, H, W, 3 * C, device="cuda", generator=g).bfloat16()
+    xm = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    b_in = torch.randn(3 * C, device="cuda", generator=g) * 0.5
+    ldo = 4 * C
+    out = torch.full((B, H, W, ldo), 7.0, device="cuda", dtype=torch.bfloat16)
+    ref = torch.full((B, H, W, ldo), 7.0, device="cuda", dtype=torch.bfloat16)
+    h.window_attention(qkv, xm, b_in, out[..., 3 * C:], B, H, W, C, wh, ww, shift)
+    h.window_attention(qkv, xm, b_in, ref[..., 3 * C:], B, H, W, C, wh, ww, shift, force_simt=True)
+    assert torch.equal(out[..., :3 * C], ref[..., :3 * C])          # nothing outside the output columns is touched
+    assert _rel(out[..., 3 * C:].float(), ref[..., 3 * C:].float()) < 6e-3
+    if shift == 0 and H % wh == 0 and W % ww == 0:
+        want = _window_attention_torch(qkv, C, wh) if wh == ww else None
+        if want is not None:
+            assert _rel(out[..., 3 * C:].float(), want) < 6e-3
+    assert h.device_fault() == 0

@@ -101,6 +101,9 @@ def test_graph_replay_matches_eager_launches(precision):
         co = _lib.DdimCoef(0.9 + 0.01 * it, 0.5, 0.4, 0.3, 0.0, int(it == 4))
         a = eager._run(x, t, coef=co, out=torch.empty_like(x), plan=plan)
         b = graph._run(x, t, coef=co, out=torch.empty_like(x), plan=plan)
-        assert torch.equal(a, b), it
+        if precision == "fp32":
+            assert torch.equal(a, b), it
+        else:   # split-K slices reduce-add into the residual stream in arrival order: equal to fp32 rounding only
+            assert R.rel_l2(a.cpu(), b.cpu()) < 5e-4, it
     assert_no_fault(graph)
     assert graph._handle.launches == eager._handle.launches
