@@ -195,6 +195,14 @@ int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float* film, voi
 int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const float* b_in, void* att, int64_t ldo,
                           int B, int H, int W, int C, int win_h, int win_w, int shift, int force_simt, void* stream);
 
+/* SwinBlock.conv (unet.py:30): x fp32 [B,H,W,C] += conv3x3(xm, groups of 32 channels, pad 1) + bias.
+ * xm [B,H,W,C] in the handle's precision.  w_packed: C % 64 == 0 -> block-diagonal pairs of groups [C/64][64][9*64]
+ * (row = output channel of the pair, column = tap*64 + input channel of the pair, zeros off the diagonal blocks);
+ * otherwise per group [C][9*32] (column = tap*32 + input channel of the group).  force_generic: the 9-tap-load
+ * implicit-GEMM kernel instead of the halo-patch kernel. */
+int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* w_packed, const float* bias, float* x, int B,
+                         int H, int W, int C, int force_generic, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

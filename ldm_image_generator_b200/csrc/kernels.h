@@ -18,6 +18,12 @@ int tc_read_fault(TcContext* ctx, cudaStream_t s);
 int tc_trace_enable(TcContext* ctx, int on);
 int tc_trace_read(TcContext* ctx, long long* host, int max_ctas);
 
+// Grouped 3x3 convolution with one halo-patch load per tile (kernels_gconv.cu): x fp32 [B,H,W,C] += conv(xm) + bias;
+// w packed as block-diagonal pairs of 32-channel groups [C/64][64][9*64].  plan: {skip,...} of the block or NULL.
+bool gconv_halo_supported(int B, int H, int W, int C);
+cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
+                              int C, const int* plan, cudaStream_t st);
+
 // ---- weight repack: dst[T] (4-d, dst strides) = src[fp32] (4-d, src strides)
 cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int dims[4],
                           const long long sstr[4], const long long dstr[4], cudaStream_t s);

@@ -1,0 +1,254 @@
+// Grouped 3x3 convolution of the SwinBlock (unet.py:30,44; groups of 32 channels) on tcgen05, reading every
+// activation ONCE: x += conv3x3_grouped(xm) + bias.
+//
+// The implicit-GEMM conv in kernels_tc.cu issues 9 shifted TMA box loads per tile (9x the activation bytes from L2,
+// which is what bounded it).  Here a tile's (TH+2) x (TW+2) halo patch of a 64-channel slice (= a pair of groups,
+// block-diagonal 64->64 weights) is loaded by ONE 4-d TMA box (out-of-bounds pixels zero-filled = the conv padding)
+// into 128-byte-swizzled shared memory, rows = patch pixels in row-major order with pitch TW+2.  Output row i of the
+// MMA tile is patch position i (y = i / (TW+2), x = i % (TW+2)), so tap (dy,dx) reads the SAME smem patch at row
+// offset dy*(TW+2)+dx: nine UMMA descriptor start addresses into one buffer, no re-load.  Rows with x >= TW or
+// y >= TH are garbage and dropped by the epilogue.  The 128-byte swizzle is a function of the shared-memory ADDRESS
+// bits (both for the TMA write and the UMMA read), so a start address that is a whole number of 128-byte rows into
+// the 1024-byte swizzle atom needs nothing else: the descriptor's base-offset field stays 0 (measured on B200:
+// setting it to (addr >> 7) & 7 gives wrong results, leaving it 0 is exact).
+// The slice's 9 x [64 x 64] weight tiles stay resident in shared memory for all tiles of a persistent CTA.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2..5 epilogue (TMEM lane quadrant each: tcgen05.ld -> + bias ->
+// red.global.add.v4.f32 into the fp32 residual stream).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tc_context.h"
+
+namespace {
+
+constexpr int kSlice = 64;                 // channels per CTA slice: two groups of 32
+constexpr int kWTile = kSlice * 128;       // one tap's [64 co x 64 ci] bf16 tile, 128 B rows
+constexpr int kWBytes = 9 * kWTile;        // 72 KB resident weights
+constexpr int kThreads = 64 + 4 * 32;
+
+struct GconvGeom {
+  int B, H, W, C;
+  int TW, TH, TB, pitch;                   // tile: TB images x TH rows x TW columns; patch pitch = TW + 2
+  int w_tiles, h_tiles, b_tiles;           // spatial tiling
+  int a_bytes, stage_bytes, stages;
+};
+
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    if (*s_abort) return false;
+    if (clock64() - t0 > 3000000000LL) {
+      *s_abort = 1;
+      atomicCAS(fault, 0, code);
+      return false;
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, float* __restrict__ x,
+                  const float* __restrict__ bias, const GconvGeom g, const int* __restrict__ plan, int* fault) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* wts = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = wts + kWBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + g.stages * g.stage_bytes);
+  uint64_t* empty = full + 4;
+  uint64_t* tfull = empty + 4;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    ptx::mbar_init(wbar, 1);
+    *s_abort = 0;
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 128); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const bool skip_block = plan != nullptr && plan[0] != 0;       // stochastic depth (unet.py:39-40)
+
+  // persistent CTA: fixed channel slice z (weights stay resident), strided over the spatial tiles
+  const int nz = g.C / kSlice;
+  const int z = blockIdx.x % nz;
+  const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;
+  const int sp0 = blockIdx.x / nz, sp_step = gridDim.x / nz;
+  const int sp_end = skip_block ? 0 : n_sp;
+
+  if (warp == 0) {
+    if (lane == 0 && sp0 < sp_end) {
+      ptx::mbar_arrive_expect_tx(wbar, kWBytes);
+      for (int tap = 0; tap < 9; ++tap) ptx::tma_load_2d(wts + tap * kWTile, &tmW, wbar, tap * kSlice, z * kSlice);
+      uint32_t stage = 0, phase = 0;
+      for (int sp = sp0; sp < sp_end; sp += sp_step) {
+        const int wt = sp % g.w_tiles, ht = (sp / g.w_tiles) % g.h_tiles, bt = sp / (g.w_tiles * g.h_tiles);
+        if (!wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 11)) break;
+        ptx::mbar_arrive_expect_tx(&full[stage], g.a_bytes);
+        ptx::tma_load_4d(stages + stage * g.stage_bytes, &tmA, &full[stage], z * kSlice, wt * g.TW - 1, ht * g.TH - 1, bt * g.TB);
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && sp0 < sp_end) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(128, kSlice);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      bool ok = wait_bar(wbar, 0, s_abort, fault, 12);
+      for (int sp = sp0; ok && sp < sp_end; sp += sp_step) {
+        if (!wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 13)) break;
+        if (!wait_bar(&full[stage], phase, s_abort, fault, 14)) break;
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(stages + stage * g.stage_bytes);
+        const uint32_t w_base = ptx::smem_u32(wts);
+        const uint32_t d_tmem = tmem_base + as * kSlice;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_addr = a_base + ((tap / 3) * g.pitch + tap % 3) * 128;
+          const uint32_t w_addr = w_base + tap * kWTile;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + k * 32), idesc,
+                          (tap | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[stage]);
+        ptx::umma_commit(&tfull[as]);
+        if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int i = q * 32 + lane;                   // output row = patch position
+    const int per_img = (g.TH + 2) * g.pitch;
+    const int img = i / per_img, r = i % per_img, yy = r / g.pitch, xx = r % g.pitch;
+    const float* bz = bias + z * kSlice;
+    uint32_t as = 0, aphase = 0;
+    for (int sp = sp0; sp < sp_end; sp += sp_step) {
+      const int wt = sp % g.w_tiles, ht = (sp / g.w_tiles) % g.h_tiles, bt = sp / (g.w_tiles * g.h_tiles);
+      const int b = bt * g.TB + img, hh = ht * g.TH + yy, ww = wt * g.TW + xx;
+      const bool valid = img < g.TB && b < g.B && yy < g.TH && hh < g.H && xx < g.TW && ww < g.W;
+      float* orow = x + (((long long)b * g.H + hh) * g.W + ww) * g.C + z * kSlice;
+      if (!wait_bar(&tfull[as], aphase, s_abort, fault, 15)) break;
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kSlice;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_row + half * 32, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + half * 32 + 4 * u));
+            red_add_v4(orow + half * 32 + 4 * u, __uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
+                       __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+static int g_gconv_mode = getenv("LDMB_GCONV_HALO") ? atoi(getenv("LDMB_GCONV_HALO")) : 1;   // debug: 0 = generic 9-tap-load kernel
+
+bool gconv_halo_supported(int B, int H, int W, int C) {
+  return g_gconv_mode != 0 && C % kSlice == 0 && C / kSlice <= 74 && B >= 1 && H >= 1 && W >= 1;
+}
+
+// x fp32 [B,H,W,C] += conv3x3(xm bf16 [B,H,W,C], grouped by 32) + bias; w packed [C/64][64][9*64] block-diagonal pairs.
+cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
+                              int C, const int* plan, cudaStream_t st) {
+  GconvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.H = H; g.W = W; g.C = C;
+  g.TW = W < 126 ? W : 126;
+  g.pitch = g.TW + 2;
+  g.TH = (128 - g.TW) / g.pitch + 1;                       // largest TH with (TH-1)*pitch + TW <= 128
+  g.TB = 1;
+  if (g.TH >= H) {
+    g.TH = H;
+    const int per_img = (H + 2) * g.pitch, last = (H - 1) * g.pitch + g.TW;   // rows used by one image
+    if (g.TW == W) g.TB = (128 - last) / per_img + 1;
+    if (g.TB > B) g.TB = B;
+  }
+  if ((long long)(g.TW + 2) > 256 || (g.TH + 2) > 256 || g.TB > 256) return cudaErrorNotSupported;
+  g.w_tiles = (W + g.TW - 1) / g.TW; g.h_tiles = (H + g.TH - 1) / g.TH; g.b_tiles = (B + g.TB - 1) / g.TB;
+  const int box_rows = g.TB * (g.TH + 2) * g.pitch;
+  g.a_bytes = box_rows * 128;
+  int need_rows = 128 + 2 * g.pitch + 2;                   // rows the nine descriptors can touch
+  if (need_rows < box_rows) need_rows = box_rows;
+  g.stage_bytes = ((need_rows * 128 + 1023) / 1024) * 1024;
+  const int avail = 232448 - 1024 - kWBytes - 256;
+  g.stages = avail / g.stage_bytes;
+  if (g.stages > 4) g.stages = 4;
+  if (g.stages < 1) return cudaErrorNotSupported;
+
+  CUtensorMap tmA, tmW;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  {
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+    const cuuint32_t box[4] = {kSlice, (cuuint32_t)g.pitch, (cuuint32_t)(g.TH + 2), (cuuint32_t)g.TB};
+    if (ctx->encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xm), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)(9 * kSlice), (cuuint64_t)C};
+    const cuuint64_t gstr[1] = {(cuuint64_t)(9 * kSlice) * 2};
+    const cuuint32_t box[2] = {kSlice, kSlice};
+    if (ctx->encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  const int smem = 1024 + kWBytes + g.stages * g.stage_bytes + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int nz = C / kSlice;
+  const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;
+  int per_z = ctx->num_sms / nz;
+  if (per_z > n_sp) per_z = n_sp;
+  if (per_z < 1) per_z = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(per_z * nz); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_ldmb_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gconv_halo_kernel, tmA, tmW, x, bias, g, plan, ctx->fault_dev);
+}

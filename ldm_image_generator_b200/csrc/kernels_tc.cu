@@ -24,17 +24,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-struct TcContext {
-  EncodeTiledFn encode;
-  int num_sms;
-  int* fault_dev;
-  int device;
-  long long* trace_dev;   // debug: per-CTA %globaltimer stamps of the last launch (NULL unless enabled)
-};
+#include "tc_context.h"
 constexpr int kTraceSlots = 16;
 
 namespace {

@@ -206,6 +206,24 @@ GemmDesc gd() {
   return d;
 }
 
+// x fp32 [B,H,W,C] += grouped conv3x3(xm) + bias (unet.py:30: groups of 32 channels).
+// tcgen05, halo-patch kernel (every activation read once) when C % 64 == 0, else the generic implicit-GEMM path.
+int grouped_conv(ldmb_handle* h, const void* xm, const void* w_g, const float* b_g, float* x, int B, int Hl, int Wl, int C,
+                 const int* pl, cudaStream_t st, bool force_generic) {
+  const int M = B * Hl * Wl;
+  if (h->bf16() && !h->force_simt && !force_generic && gconv_halo_supported(B, Hl, Wl, C)) {
+    CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim, launch_gconv_halo(h->tc, xm, w_g, b_g, x, B, Hl, Wl, C, pl, st));
+    return LDMB_OK;
+  }
+  GemmDesc d = gd();
+  const int gw = (C % 64 == 0) ? 64 : kHeadDim;          // channels per launch-batch: a pair of groups, or one group
+  d.A = xm; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = gw;
+  d.W = w_g; d.ldw = 9 * gw; d.bias = b_g; d.out = x; d.ldo = C;
+  d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32; d.plan = pl;
+  d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
+  return gemm(h, d, st, PK_GCONV);
+}
+
 // ---------------------------------------------------------------- repack helpers
 int repack(ldmb_handle* h, const float* src, void* dst, bool to_t, int d0, int d1, int d2, long long s0, long long s1,
            long long s2, long long t0, long long t1, long long t2, cudaStream_t st) {
@@ -622,16 +640,8 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, pl, st));
-  // grouped 3x3 (unet.py:30): x += conv(xm) (TMA fp32 reduce-add on the tcgen05 path; x is not read)
-  {
-    GemmDesc d = gd();
-    const int gw = (C % 64 == 0) ? 64 : kHeadDim;          // channels per launch-batch: a pair of groups, or one group
-    d.A = u.xm.p; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = gw;
-    d.W = w.w_g; d.ldw = 9 * gw; d.bias = w.b_g; d.out = x; d.ldo = C;
-    d.M = M; d.N = gw; d.K = 9 * gw; d.epi = EPI_ACCUM_F32; d.plan = pl;
-    d.batch = C / gw; d.a_koff_b = gw; d.w_row_b = gw; d.out_off_b = gw; d.bias_off_b = gw;
-    if ((rc = gemm(h, d, st, PK_GCONV))) return rc;
-  }
+  // grouped 3x3 (unet.py:30): x += conv(xm); the residual stream is only ever added to (x itself is not read)
+  if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
@@ -1151,4 +1161,11 @@ extern "C" int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void
        launch_window_attention(qkv, xm, b_in, att, ldo, h->bf16(), B, H, W, C, kHeadDim, win_h, win_w, shift, nullptr, st,
                                force_simt != 0));
   return LDMB_OK;
+}
+
+extern "C" int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* w_packed, const float* bias, float* x, int B,
+                                    int H, int W, int C, int force_generic, void* stream) {
+  if (!h || !xm || !w_packed || !bias || !x || B < 1 || H < 1 || W < 1 || C < kHeadDim || C % kHeadDim) return LDMB_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  return grouped_conv(h, xm, w_packed, bias, x, B, H, W, C, nullptr, static_cast<cudaStream_t>(stream), force_generic != 0);
 }

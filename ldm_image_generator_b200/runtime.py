@@ -196,6 +196,10 @@ class Handle:
         self.check(self.lib.ldmb_conv3x3(self.h, x.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
                                          out.data_ptr(), B, H, W, Cc, N, act, int(force_simt), stream_ptr(self.device)))
 
+    def grouped_conv3x3(self, xm, w_packed, bias, x, B, H, W, Cc, force_generic=False) -> None:
+        self.check(self.lib.ldmb_grouped_conv3x3(self.h, xm.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                                 B, H, W, Cc, int(force_generic), stream_ptr(self.device)))
+
     def window_attention(self, qkv, xm, b_in, att, B, H, W, Cc, win_h, win_w, shift, force_simt=False) -> None:
         self.check(self.lib.ldmb_window_attention(self.h, qkv.data_ptr(), xm.data_ptr(), b_in.data_ptr(), att.data_ptr(),
                                                   att.stride(-2), B, H, W, Cc, win_h, win_w, shift, int(force_simt),

@@ -150,3 +150,31 @@ def test_window_attention_mma_kernel(handles, B, H, W, C, wh, ww, shift):
         if want is not None:
             assert _rel(out[..., 3 * C:].float(), want) < 6e-3
     assert h.device_fault() == 0
+
+
+def _pack_grouped(w):
+    """[C, 32, 3, 3] grouped-conv weight -> block-diagonal pairs [C/64][64][9*64] (ldmb.h: ldmb_grouped_conv3x3)."""
+    C = w.shape[0]
+    out = torch.zeros(C // 64, 64, 9, 64, device=w.device, dtype=w.dtype)
+    wp = w.reshape(C // 64, 2, 32, 32, 9)                       # pair, group-in-pair, co, ci, tap
+    for gl in range(2):
+        out[:, gl * 32:(gl + 1) * 32, :, gl * 32:(gl + 1) * 32] = wp[:, gl].permute(0, 1, 3, 2)
+    return out.reshape(C, 9 * 64).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (3, 16, 16, 256), (5, 8, 8, 512), (7, 4, 4, 1024), (2, 20, 28, 128),
+                                     (1, 64, 64, 256), (3, 5, 3, 64), (64, 8, 8, 512)])
+@pytest.mark.parametrize("generic", [False, True])
+def test_grouped_conv3x3_accumulates_into_residual(handles, B, H, W, C, generic):
+    """unet.py:30 on NHWC: halo-patch tcgen05 kernel (and the generic 9-tap-load kernel) vs F.conv2d(groups=C/32)."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H * 3 + W + C)
+    xm = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 32, 3, 3, device="cuda", generator=g) / 288 ** 0.5).bfloat16()
+    b = torch.randn(C, device="cuda", generator=g)
+    x0 = torch.randn(B, H, W, C, device="cuda", generator=g)
+    x = x0.clone()
+    h.grouped_conv3x3(xm, _pack_grouped(w), b, x, B, H, W, C, force_generic=generic)
+    ref = F.conv2d(xm.float().permute(0, 3, 1, 2), w.float(), b, padding=1, groups=C // 32).permute(0, 2, 3, 1)
+    assert h.device_fault() == 0
+    assert _rel(x - x0, ref) < 1e-5
