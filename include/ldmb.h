@@ -153,11 +153,18 @@ int ldmb_unet_set_position_table(ldmb_handle* h, int level, const float* pe_host
  *   plan       host int32 [n_blocks][3] = (skip, e1, e2) per SwinBlock in execution order: the Python
  *              `random` decisions of unet.py:39 and modules.py:35, drawn by the caller in lock-step
  *   noise_dev  [B, Cin, H, W] or NULL (required only when coef->sigma != 0)
+ * te_host == NULL: the FiLM tables of the n_t timesteps registered by ldmb_unet_precompute_film are used (t_index
+ * indexes that table) and the Encodings MLP is not evaluated by this call.
  */
 int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
                       const int32_t* t_index, int n_t, const float* const* te_host,
                       const int32_t* plan, const ldmb_ddim_coef* coef, const float* noise_dev,
                       void* stream);
+
+/* The Encodings MLP (unet.py:18-21) of every block for ALL n_t timesteps of a sampling schedule in one batched pass
+ * (its weights, 58 % of the parameters, are then streamed once per schedule instead of once per step).
+ * te_host as in ldmb_unet_forward.  Valid until the next ldmb_unet_load_param / ldmb_unet_forward with te_host != NULL. */
+int ldmb_unet_precompute_film(ldmb_handle* h, int H, int W, int n_t, const float* const* te_host, void* stream);
 
 /* ---------------------------------------------------------------- VAE (vae.py) */
 int ldmb_vae_configure(ldmb_handle* h, int which, const ldmb_vae_config* cfg);

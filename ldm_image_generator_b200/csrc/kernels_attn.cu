@@ -80,114 +80,101 @@ __global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
     kb[tid] = bias;
   }
   __syncthreads();
-  // ---- gather q | k | v rows of this (window, head chunk): 16 x 16-byte pieces per token per matrix
+  // ---- gather q | k | v rows of this (window, head chunk): 16 x 16-byte pieces per token per matrix, all in flight
+  //      at once as asynchronous global->shared copies (the CTA is otherwise one dependent-load latency per piece)
   for (int idx = tid; idx < LP * 3 * (kRow / 8); idx += 32 * kHC) {
     const int piece = idx % (kRow / 8), which = (idx / (kRow / 8)) % 3, tok = idx / (3 * (kRow / 8));
     const long long m = rowm[tok];
     bf16* dst = (which == 0 ? Qs : (which == 1 ? Ks : Vs)) + tok * kLd + piece * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (m >= 0) {
-      v = __ldg(reinterpret_cast<const uint4*>(qkv + m * 3 * C + (long long)which * C + ch0 + piece * 8));
-    } else if (m == -1 && which != 0) {                     // pad token: x = 0 -> k, v = in_proj bias (attention.py:19-23)
-      const float* bp = b_in + which * C + ch0 + piece * 8;
-      v.x = pack2(bp[0], bp[1]); v.y = pack2(bp[2], bp[3]); v.z = pack2(bp[4], bp[5]); v.w = pack2(bp[6], bp[7]);
+      const bf16* src = qkv + m * 3 * C + (long long)which * C + ch0 + piece * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+    } else {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (m == -1 && which != 0) {                          // pad token: x = 0 -> k, v = in_proj bias (attention.py:19-23)
+        const float* bp = b_in + which * C + ch0 + piece * 8;
+        v.x = pack2(bp[0], bp[1]); v.y = pack2(bp[2], bp[3]); v.z = pack2(bp[4], bp[5]); v.w = pack2(bp[6], bp[7]);
+      }
+      *reinterpret_cast<uint4*>(dst) = v;
     }
-    *reinterpret_cast<uint4*>(dst) = v;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int g = lane >> 2, t4 = lane & 3;
   const int hc = warp * kD;                                 // this warp's head: columns [hc, hc + 32)
-  // ---- S = q k^T
-  uint32_t qa[MT][2][4];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  // One 16-query tile at a time (K / V fragments are re-read from shared memory per tile): keeps the live state to
+  // one S row-block + one O row-block so several CTAs fit an SM's register file.
+  const float scale_l2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
+#pragma unroll 1
+  for (int mt = 0; mt < MT; ++mt) {
+    // ---- S = q k^T
+    uint32_t qa[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = hc + ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Qs + row * kLd + col)), qa[mt][ks][0], qa[mt][ks][1], qa[mt][ks][2],
-              qa[mt][ks][3]);
+      ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Qs + row * kLd + col)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
     }
-  float s[MT][NT][4];
+    float s[NT][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    uint32_t kf[4];
-    {
+    for (int nt = 0; nt < NT; ++nt) {
+      uint32_t kf[4];
       const int row = nt * 8 + (lane & 7), col = hc + (lane >> 3) * 8;
       ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Ks + row * kLd + col)), kf[0], kf[1], kf[2], kf[3]);
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      mma_bf16(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kf[0], kf[1]);
+      mma_bf16(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kf[2], kf[3]);
     }
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
-      mma_bf16(s[mt][nt], qa[mt][0][0], qa[mt][0][1], qa[mt][0][2], qa[mt][0][3], kf[0], kf[1]);
-      mma_bf16(s[mt][nt], qa[mt][1][0], qa[mt][1][1], qa[mt][1][2], qa[mt][1][3], kf[2], kf[3]);
-    }
-  }
-  // ---- softmax over keys (rows g and g+8 of every 16-row tile; a row is spread over the 4 lanes of a quad)
-  const float scale_l2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
-  float inv[MT][2];
-  uint32_t pa[MT][MT][4];                                    // P as A fragments of the second product
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
+    // ---- softmax over keys (rows g and g+8 of the tile; a row is spread over the 4 lanes of a quad)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const float b0 = kb[nt * 8 + 2 * t4] * 1.4426950408889634f, b1 = kb[nt * 8 + 2 * t4 + 1] * 1.4426950408889634f;
-      s[mt][nt][0] = fmaf(s[mt][nt][0], scale_l2, b0); s[mt][nt][1] = fmaf(s[mt][nt][1], scale_l2, b1);
-      s[mt][nt][2] = fmaf(s[mt][nt][2], scale_l2, b0); s[mt][nt][3] = fmaf(s[mt][nt][3], scale_l2, b1);
-      mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+      s[nt][0] = fmaf(s[nt][0], scale_l2, b0); s[nt][1] = fmaf(s[nt][1], scale_l2, b1);
+      s[nt][2] = fmaf(s[nt][2], scale_l2, b0); s[nt][3] = fmaf(s[nt][3], scale_l2, b1);
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      s[mt][nt][0] = exp2f(s[mt][nt][0] - mx0); s[mt][nt][1] = exp2f(s[mt][nt][1] - mx0);
-      s[mt][nt][2] = exp2f(s[mt][nt][2] - mx1); s[mt][nt][3] = exp2f(s[mt][nt][3] - mx1);
-      sum0 += s[mt][nt][0] + s[mt][nt][1];
-      sum1 += s[mt][nt][2] + s[mt][nt][3];
+      s[nt][0] = exp2f(s[nt][0] - mx0); s[nt][1] = exp2f(s[nt][1] - mx0);
+      s[nt][2] = exp2f(s[nt][2] - mx1); s[nt][3] = exp2f(s[nt][3] - mx1);
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    inv[mt][0] = 1.f / sum0; inv[mt][1] = 1.f / sum1;
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    // ---- O = P v (P re-used from the S accumulators as A fragments)
+    float o[4][4];
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
 #pragma unroll
     for (int kt = 0; kt < MT; ++kt) {
-      pa[mt][kt][0] = pack2(s[mt][2 * kt][0], s[mt][2 * kt][1]);
-      pa[mt][kt][1] = pack2(s[mt][2 * kt][2], s[mt][2 * kt][3]);
-      pa[mt][kt][2] = pack2(s[mt][2 * kt + 1][0], s[mt][2 * kt + 1][1]);
-      pa[mt][kt][3] = pack2(s[mt][2 * kt + 1][2], s[mt][2 * kt + 1][3]);
-    }
-  }
-  // ---- O = P v
-  float o[MT][4][4];
+      const uint32_t p0 = pack2(s[2 * kt][0], s[2 * kt][1]), p1 = pack2(s[2 * kt][2], s[2 * kt][3]);
+      const uint32_t p2 = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]), p3 = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int dt = 0; dt < 4; ++dt) o[mt][dt][0] = o[mt][dt][1] = o[mt][dt][2] = o[mt][dt][3] = 0.f;
-#pragma unroll
-  for (int kt = 0; kt < MT; ++kt)
-#pragma unroll
-    for (int dp = 0; dp < 2; ++dp) {                         // pairs of 8-wide d tiles
-      uint32_t vf[4];
-      const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = hc + (dp * 2 + (lane >> 4)) * 8;
-      ldsm_x4_t(static_cast<uint32_t>(__cvta_generic_to_shared(Vs + row * kLd + col)), vf[0], vf[1], vf[2], vf[3]);
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        mma_bf16(o[mt][dp * 2], pa[mt][kt][0], pa[mt][kt][1], pa[mt][kt][2], pa[mt][kt][3], vf[0], vf[1]);
-        mma_bf16(o[mt][dp * 2 + 1], pa[mt][kt][0], pa[mt][kt][1], pa[mt][kt][2], pa[mt][kt][3], vf[2], vf[3]);
+      for (int dp = 0; dp < 2; ++dp) {                       // pairs of 8-wide d tiles
+        uint32_t vf[4];
+        const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = hc + (dp * 2 + (lane >> 4)) * 8;
+        ldsm_x4_t(static_cast<uint32_t>(__cvta_generic_to_shared(Vs + row * kLd + col)), vf[0], vf[1], vf[2], vf[3]);
+        mma_bf16(o[dp * 2], p0, p1, p2, p3, vf[0], vf[1]);
+        mma_bf16(o[dp * 2 + 1], p0, p1, p2, p3, vf[2], vf[3]);
       }
     }
-  // ---- stage this head's output over its own (consumed) q columns, then coalesced row stores
-  __syncwarp();
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+    // ---- stage this head's output over its own (consumed) q rows of this tile
+    __syncwarp();
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
-      bf16* p0 = Qs + (mt * 16 + g) * kLd + hc + dt * 8 + 2 * t4;
-      *reinterpret_cast<uint32_t*>(p0) = pack2(o[mt][dt][0] * inv[mt][0], o[mt][dt][1] * inv[mt][0]);
-      *reinterpret_cast<uint32_t*>(p0 + 8 * kLd) = pack2(o[mt][dt][2] * inv[mt][1], o[mt][dt][3] * inv[mt][1]);
+      bf16* q0 = Qs + (mt * 16 + g) * kLd + hc + dt * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(q0) = pack2(o[dt][0] * inv0, o[dt][1] * inv0);
+      *reinterpret_cast<uint32_t*>(q0 + 8 * kLd) = pack2(o[dt][2] * inv1, o[dt][3] * inv1);
     }
+  }
   __syncthreads();
   for (int idx = tid; idx < L * (kRow / 8); idx += 32 * kHC) {
     const int piece = idx % (kRow / 8), tok = idx / (kRow / 8);

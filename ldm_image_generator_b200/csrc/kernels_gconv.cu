@@ -34,6 +34,7 @@ struct GconvGeom {
   int TW, TH, TB, pitch;                   // tile: TB images x TH rows x TW columns; patch pitch = TW + 2
   int w_tiles, h_tiles, b_tiles;           // spatial tiling
   int a_bytes, stage_bytes, stages;
+  int dbg;                                 // debug experiments: 1 = no reds, 2 = one tap only
 };
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
@@ -50,13 +51,21 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatil
   }
 }
 
+__device__ __forceinline__ void trace_stamp(long long* trace, int slot) {     // debug: same 16-slot layout as kernels_tc.cu
+  if (trace != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[blockIdx.x * 16 + slot] = t;
+  }
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, float* __restrict__ x,
-                  const float* __restrict__ bias, const GconvGeom g, const int* __restrict__ plan, int* fault) {
+                  const float* __restrict__ bias, const GconvGeom g, const int* __restrict__ plan, int* fault, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wts = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = wts + kWBytes;
@@ -69,6 +78,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (threadIdx.x == 0) trace_stamp(trace, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
@@ -83,8 +93,10 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
+  // plan and weights are older than the previous kernel: read / requested before waiting on it
   const bool skip_block = plan != nullptr && plan[0] != 0;       // stochastic depth (unet.py:39-40)
+  const bool is_producer = warp == 0 && lane == 0;
+  if (!is_producer) pdl_wait();
 
   // persistent CTA: fixed channel slice z (weights stay resident), strided over the spatial tiles
   const int nz = g.C / kSlice;
@@ -97,14 +109,20 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0 && sp0 < sp_end) {
       ptx::mbar_arrive_expect_tx(wbar, kWBytes);
       for (int tap = 0; tap < 9; ++tap) ptx::tma_load_2d(wts + tap * kWTile, &tmW, wbar, tap * kSlice, z * kSlice);
+      trace_stamp(trace, 1);
+      pdl_wait();
+      trace_stamp(trace, 2);
       uint32_t stage = 0, phase = 0;
       for (int sp = sp0; sp < sp_end; sp += sp_step) {
         const int wt = sp % g.w_tiles, ht = (sp / g.w_tiles) % g.h_tiles, bt = sp / (g.w_tiles * g.h_tiles);
         if (!wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 11)) break;
         ptx::mbar_arrive_expect_tx(&full[stage], g.a_bytes);
         ptx::tma_load_4d(stages + stage * g.stage_bytes, &tmA, &full[stage], z * kSlice, wt * g.TW - 1, ht * g.TH - 1, bt * g.TB);
+        if (sp == sp0) trace_stamp(trace, 3);
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
       }
+    } else if (lane == 0) {
+      pdl_wait();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -112,15 +130,17 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = ptx::idesc_bf16(128, kSlice);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       bool ok = wait_bar(wbar, 0, s_abort, fault, 12);
+      trace_stamp(trace, 10);
       for (int sp = sp0; ok && sp < sp_end; sp += sp_step) {
         if (!wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 13)) break;
         if (!wait_bar(&full[stage], phase, s_abort, fault, 14)) break;
+        if (sp == sp0) trace_stamp(trace, 4);
         ptx::tc_fence_after();
         const uint32_t a_base = ptx::smem_u32(stages + stage * g.stage_bytes);
         const uint32_t w_base = ptx::smem_u32(wts);
         const uint32_t d_tmem = tmem_base + as * kSlice;
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < ((g.dbg & 2) ? 1 : 9); ++tap) {
           const uint32_t a_addr = a_base + ((tap / 3) * g.pitch + tap % 3) * 128;
           const uint32_t w_addr = w_base + tap * kWTile;
 #pragma unroll
@@ -134,6 +154,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
+      trace_stamp(trace, 5);
     }
     __syncwarp();
   } else {
@@ -149,6 +170,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = img < g.TB && b < g.B && yy < g.TH && hh < g.H && xx < g.TW && ww < g.W;
       float* orow = x + (((long long)b * g.H + hh) * g.W + ww) * g.C + z * kSlice;
       if (!wait_bar(&tfull[as], aphase, s_abort, fault, 15)) break;
+      if (threadIdx.x == 64) trace_stamp(trace, sp == sp0 ? 6 : 7);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kSlice;
 #pragma unroll
@@ -156,7 +178,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_row + half * 32, v);
         ptx::tmem_ld_wait();
-        if (valid) {
+        if (valid && !(g.dbg & 1)) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + half * 32 + 4 * u));
@@ -172,9 +194,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (as == 0) aphase ^= 1;
     }
   }
+  if (threadIdx.x == 64) trace_stamp(trace, 8);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 128);
+  if (threadIdx.x == 0) trace_stamp(trace, 9);
 }
 
 }  // namespace
@@ -213,6 +237,7 @@ cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, con
   if (g.stages > 4) g.stages = 4;
   if (g.stages < 1) return cudaErrorNotSupported;
 
+  g.dbg = getenv("LDMB_GCONV_DBG") ? atoi(getenv("LDMB_GCONV_DBG")) : 0;
   CUtensorMap tmA, tmW;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   {
@@ -250,5 +275,5 @@ cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, con
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_ldmb_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gconv_halo_kernel, tmA, tmW, x, bias, g, plan, ctx->fault_dev);
+  return cudaLaunchKernelEx(&cfg, gconv_halo_kernel, tmA, tmW, x, bias, g, plan, ctx->fault_dev, ctx->trace_dev);
 }

@@ -457,14 +457,14 @@ __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restri
   const int J = Cin * s * s;
   float* xs = smem_in;                    // [kPixIn][J + 1]
   float* ws = smem_in + kPixIn * (J + 1); // [J][Cout]  (transposed: consecutive threads read consecutive channels)
-  const long long M = (long long)B * H * W, m0 = (long long)blockIdx.x * kPixIn;
+  const int M = B * H * W, m0 = blockIdx.x * kPixIn;     // 32-bit pixel index (64-bit divisions are slow)
   for (int i = threadIdx.x; i < Cout * J; i += blockDim.x) ws[(i % J) * Cout + i / J] = w[i];
   for (int i = threadIdx.x; i < kPixIn * J; i += blockDim.x) {
     const int p = i % kPixIn, j = i / kPixIn;           // consecutive threads -> consecutive pixels (contiguous along w)
-    const long long m = m0 + p;
+    const int m = m0 + p;
     float v = 0.f;
     if (m < M) {
-      const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
+      const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
       const int ci = j / (s * s), dy = (j / s) % s, dx = j % s;
       v = x[(((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx];
     }
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restri
     const int q = Cout >> 2;                             // channel quads per pixel
     for (int i = threadIdx.x; i < kPixIn * q; i += blockDim.x) {
       const int p = i / q, co = (i % q) * 4;
-      const long long m = m0 + p;
+      const int m = m0 + p;
       if (m >= M) break;
       float4 acc = *reinterpret_cast<const float4*>(bias + co);
       const float* xr = xs + p * (J + 1);
@@ -484,18 +484,18 @@ __global__ void __launch_bounds__(256) pointwise_in_kernel(const float* __restri
         const float4 wv = *reinterpret_cast<const float4*>(ws + j * Cout + co);
         acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
       }
-      Pack4<TO>::store(out + m * Cout + co, acc.x, acc.y, acc.z, acc.w);
+      Pack4<TO>::store(out + (long long)m * Cout + co, acc.x, acc.y, acc.z, acc.w);
     }
     return;
   }
   for (int i = threadIdx.x; i < kPixIn * Cout; i += blockDim.x) {
     const int p = i / Cout, co = i % Cout;
-    const long long m = m0 + p;
+    const int m = m0 + p;
     if (m >= M) break;
     float acc = bias[co];
     const float* xr = xs + p * (J + 1);
     for (int j = 0; j < J; ++j) acc = fmaf(xr[j], ws[j * Cout + co], acc);
-    out[m * Cout + co] = from_f<TO>(acc);
+    out[(long long)m * Cout + co] = from_f<TO>(acc);
   }
 }
 
@@ -601,49 +601,64 @@ __global__ void __launch_bounds__(256) final_warp_kernel(const float* __restrict
   // output owned by this lane after the fold: bit 4 -> +4, bit 3 -> +2, bit 2 -> +1
   const int jl = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const float bj = jl < J ? bias[jl / (s * s)] : 0.f;
-  const long long M = (long long)B * H * W;
-  const long long wpg = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += wpg) {
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int M = B * H * W;                                // 32-bit pixel index: 64-bit divisions cost ~100 instructions each
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  constexpr int PX = 4;                                   // pixels per warp iteration: PX independent row loads in flight
+  const bool owner = (lane & 3) == 0 && jl < J;
+  const int ci = jl / (s * s), dy = (jl / s) % s, dx = jl % s;
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PX; mb < M; mb += wpg * PX) {
+    float4 v[PX][V];
+    long long o[PX];
+    float xi[PX];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + m * C0 + i * 128 + lane * 4));
+    for (int p = 0; p < PX; ++p) {
+      const int m = mb + p;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        a[j] = fmaf(v.x, wr[j][4 * i], fmaf(v.y, wr[j][4 * i + 1], fmaf(v.z, wr[j][4 * i + 2], fmaf(v.w, wr[j][4 * i + 3], a[j]))));
+      for (int i = 0; i < V; ++i)
+        v[p][i] = m < M ? __ldg(reinterpret_cast<const float4*>(x + (long long)m * C0 + i * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
+      o[p] = (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
+      xi[p] = (owner && m < M && co.ddim_enabled) ? xin[o[p]] : 0.f;
     }
-    {
-      const bool hi = lane & 16;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 16); a[i] = (hi ? a[i + 4] : a[i]) + r; }
-    }
-    {
-      const bool hi = lane & 8;
+    for (int p = 0; p < PX; ++p) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 2], 8); a[i] = (hi ? a[i + 2] : a[i]) + r; }
-    }
-    {
-      const bool hi = lane & 4;
-      const float r = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[1], 4);
-      a[0] = (hi ? a[1] : a[0]) + r;
-    }
-    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
-    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-    if ((lane & 3) == 0 && jl < J) {
-      const int ci = jl / (s * s), dy = (jl / s) % s, dx = jl % s;
-      const int ww = (int)(m % W), hh = (int)((m / W) % H), b = (int)(m / ((long long)W * H));
-      const long long o = (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
-      const float eps = a[0] + bj;
-      float r = eps;
-      if (co.ddim_enabled) {
-        const float x0 = (xin[o] - co.c_eps_in * eps) / co.c_div;
-        if (co.final_step) r = x0;
-        else {
-          r = co.c_x0 * x0 + co.c_eps_out * eps;
-          r += co.sigma * (noise ? noise[o] : 0.f);
-        }
+      for (int i = 0; i < V; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          a[j] = fmaf(v[p][i].x, wr[j][4 * i], fmaf(v[p][i].y, wr[j][4 * i + 1], fmaf(v[p][i].z, wr[j][4 * i + 2], fmaf(v[p][i].w, wr[j][4 * i + 3], a[j]))));
       }
-      out[o] = r;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 16); a[i] = (hi ? a[i + 4] : a[i]) + r; }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { const float r = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 2], 8); a[i] = (hi ? a[i + 2] : a[i]) + r; }
+      }
+      {
+        const bool hi = lane & 4;
+        const float r = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[1], 4);
+        a[0] = (hi ? a[1] : a[0]) + r;
+      }
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+      if (owner && mb + p < M) {
+        const float eps = a[0] + bj;
+        float r = eps;
+        if (co.ddim_enabled) {
+          const float x0 = (xi[p] - co.c_eps_in * eps) / co.c_div;
+          if (co.final_step) r = x0;
+          else {
+            r = co.c_x0 * x0 + co.c_eps_out * eps;
+            r += co.sigma * (noise ? noise[o[p]] : 0.f);
+          }
+        }
+        out[o[p]] = r;
+      }
     }
   }
 }
@@ -832,7 +847,7 @@ cudaError_t launch_final(const float* x, const float* w, const float* bias, cons
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
   if (Cin * s * s <= 8 && (C0 == 128 || C0 == 256)) {
-    const int grid = grid_for(M * 32, 256, 148 * 4);
+    const int grid = grid_for(M * 8, 256, 148 * 8);
     if (C0 == 128) launch_k((final_warp_kernel<1>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
     else launch_k((final_warp_kernel<2>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);
     return cudaGetLastError();

@@ -130,8 +130,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_per_split = tl.total / tl.splits;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail.
   if (threadIdx.x == 0) trace_stamp(trace, 1);                 // setup done
-  pdl_wait();
-  if (threadIdx.x == 0) trace_stamp(trace, 2);                 // previous kernel complete
+  // The step's plan entry was uploaded before the first kernel of the step (an ancestor of every kernel in the
+  // stream / graph), so it is read BEFORE waiting on the previous kernel, like the weights (see the producer).
   // expert rows of the (up to 4) selection slots, resolved from the device-side plan when there is one
   int srow0 = d.sel_rows[0], srow1 = d.sel_rows[1], srow2 = d.sel_rows[2], srow3 = d.sel_rows[3];
   bool skip_block = false;
@@ -141,10 +141,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   auto srow = [&](int q) { return q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3)); };
   const int total_tiles = skip_block ? 0 : tl.total;
+  const bool is_producer = warp == 0 && lane == 0;
+  if (!is_producer) {
+    pdl_wait();
+    if (threadIdx.x == 32) trace_stamp(trace, 2);              // previous kernel complete
+  }
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
+      auto b_coords = [&](int z, int n0, int kk, int& brow, int& bcol) {
+        bcol = kk;
+        if (d.sel == 2) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
+        else if (d.sel == 1) brow = srow(n0 / d.sel_span) + n0 % d.sel_span;
+        else brow = n0;
+        brow += (int)(z * d.w_row_b) + (int)rank * Cfg::B_ROWS;      // this CTA's share of the tile's weight rows
+      };
+      // Weights are never written by a kernel of the step: the B tiles of the first pipeline fill are requested
+      // while the previous kernel is still draining; only the activation (A) loads wait for it.
+      int pre = 0;
+      {
+        const int t = blockIdx.x / CG;
+        if (t < total_tiles) {
+          const int sp = t / tiles_per_split, ts = t % tiles_per_split;
+          const int z = ts / tiles_per_z, nt = (ts % tiles_per_z) % tl.n_tiles;
+          const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
+          for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
+            uint8_t* b_dst = tiles + pre * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+            if (leader) ptx::mbar_arrive_expect_tx(&full[pre], Cfg::STAGE_BYTES * CG);
+            int brow, bcol;
+            b_coords(z, nt * BN, kb * BK, brow, bcol);
+            if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[pre], bcol, brow);
+            else ptx::tma_load_2d(b_dst, &tmB, &full[pre], bcol, brow);
+          }
+        }
+      }
+      pdl_wait();
+      trace_stamp(trace, 2);                                     // previous kernel complete (producer's view)
       uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
         const int sp = t / tiles_per_split, ts = t % tiles_per_split;
@@ -161,10 +194,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           w0 = r % d.cW;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
-          wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
+          const bool b_done = pre > 0;                          // this stage's B tile (and expect_tx) was issued up front
+          if (b_done) --pre;
+          else wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-          if (leader) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
+          if (leader && !b_done) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
           const int kk = kb * BK;
           if (AMODE == AM_ROWS) {
             if (CG == 2) ptx::tma_load_2d_2sm(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
@@ -174,13 +209,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CG == 2) ptx::tma_load_4d_2sm(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
             else ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
           }
-          int brow, bcol = kk;
-          if (d.sel == 2) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
-          else if (d.sel == 1) brow = srow(n0 / d.sel_span) + n0 % d.sel_span;
-          else brow = n0;
-          brow += (int)(z * d.w_row_b) + (int)rank * Cfg::B_ROWS;      // this CTA's share of the tile's weight rows
-          if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
-          else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
+          if (!b_done) {
+            int brow, bcol;
+            b_coords(z, n0, kk, brow, bcol);
+            if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
+            else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
+          }
           if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 3);   // first loads issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -495,15 +529,6 @@ int pick_bn(const GemmDesc& d, int num_sms) {
     if (d.epi == EPI_REGLU && bn < 128) return false;
     return true;
   };
-  // Few-row GEMMs (the hoisted Encodings MLP, the level-change 1x1 convs: M <= 128) stream their weights once
-  // from HBM: what matters is enough CTAs to pull the full HBM bandwidth, so take the widest tile that still gives
-  // every SM a CTA (else the narrowest).
-  if (m_tiles == 1 && d.sel == 0 && d.epi != EPI_REGLU) {
-    for (int bn : {256, 128, 64})
-      if (ok(bn) && (long long)((d.N + bn - 1) / bn) * batch >= num_sms) return bn;
-    for (int bn : {64, 128, 256}) if (ok(bn)) return bn;
-    return 0;
-  }
   if (ok(256)) return 256;       // the widest tile: L2->SM bytes per FLOP decide the main-loop rate
   if (ok(128)) return 128;
   if (ok(64)) return 64;

@@ -82,10 +82,12 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, pooled, ylow, stepbuf;
+  DevBuf xm, hbuf, qkv, pooled, ylow, stepbuf, te_pre;
+  // FiLM tables precomputed for a whole schedule (ldmb_unet_precompute_film): film holds n_t = film_nt timesteps
+  int film_nt = 0, film_Hs = 0, film_Ws = 0;
   // device views into stepbuf (layout fixed per (B, n_t)): StepParams | plan[n_blocks][4] | t_index[B] | te tables
   const StepParams* sp_dev = nullptr; const int* plan_dev = nullptr; const int* tindex_dev = nullptr;
-  struct GraphEntry { int B, Hs, Ws, n_t; unsigned long long epoch; cudaGraphExec_t exec; long long launches; int seen; };
+  struct GraphEntry { int B, Hs, Ws, n_t, pre; unsigned long long epoch; cudaGraphExec_t exec; long long launches; int seen; };
   std::vector<GraphEntry> graphs;
   unsigned long long ws_epoch = 0;     // bumped whenever a workspace is reallocated (cached graphs hold raw pointers)
   bool use_graphs = true;
@@ -288,7 +290,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf); release(u.te_pre);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
   if (u.staging) {
@@ -458,6 +460,7 @@ extern "C" int ldmb_unet_load_param(ldmb_handle* h, const char* name, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const ldmb_unet_config& cfg = u.cfg;
   const int S = cfg.num_levels, s = cfg.stem_size, Cin = cfg.input_channels, C0 = cfg.channels[0];
+  u.film_nt = 0;                       // FiLM tables depend on the Encodings weights
   std::string nm(name);
   if (nm.rfind("model.", 0) == 0) nm = nm.substr(6);
   auto bad_shape = [&]() { return fail(h, LDMB_ERR_INVALID, "size mismatch for %s", name); };
@@ -672,26 +675,32 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
 
 // Every launch of one UNet step, in order, on `st`.  Static given (B, Hs, Ws, n_t): all per-step values are read from
 // the device-side step buffer, so the sequence can be captured once into a CUDA graph and replayed.
-int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* const* te_dev, cudaStream_t st) {
+// Encodings (unet.py:18-21) of one level, hoisted: the FiLM rows depend on (t,h,w) only -> one evaluation for all
+// blocks of the level and all n_t timesteps: film[block][t][pixel][mul | bias].
+int issue_encodings(ldmb_handle* h, int l, int HW, int n_t, const float* te_dev, cudaStream_t st) {
+  LevelW& L = h->unet.levels[l];
+  const int C = L.C, Mt = n_t * HW;
+  int rc;
+  CKL(launch_emb_build(static_cast<const float*>(L.pe.p), te_dev, L.emb.p, h->bf16(), n_t, HW, C, st));
+  GemmDesc a = gd();
+  a.A = L.emb.p; a.lda = 2 * C; a.W = L.w1; a.ldw = 2 * C; a.bias = L.b1; a.out = L.h1.p; a.ldo = (long long)L.nb * 4 * C;
+  a.M = Mt; a.N = L.nb * 4 * C; a.K = 2 * C; a.epi = EPI_STORE; a.act = ACT_RELU;
+  if ((rc = gemm(h, a, st, PK_ENC))) return rc;
+  GemmDesc b = gd();
+  b.A = L.h1.p; b.lda = (long long)L.nb * 4 * C; b.W = L.w2; b.ldw = 4 * C; b.bias = L.b2; b.out = L.film.p; b.ldo = 2 * C;
+  b.M = Mt; b.N = 2 * C; b.K = 4 * C; b.epi = EPI_STORE_F32;
+  b.batch = L.nb; b.a_koff_b = 4 * C; b.w_row_b = 2 * C; b.out_off_b = (long long)Mt * 2 * C; b.bias_off_b = 2 * C;
+  return gemm(h, b, st, PK_ENC);
+}
+
+int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* const* te_dev, cudaStream_t st, bool pre) {
   UNetState& u = h->unet;
   const ldmb_unet_config& cfg = u.cfg;
   const int S = cfg.num_levels, s = cfg.stem_size;
   int rc;
-  // ---- Encodings (unet.py:18-21), hoisted: depends on (t,h,w) only -> once per call for all blocks of a level
-  for (int l = 0; l < S; ++l) {
-    LevelW& L = u.levels[l];
-    const int C = L.C, HW = (Hs >> l) * (Ws >> l), Mt = n_t * HW;
-    CKL(launch_emb_build(static_cast<const float*>(L.pe.p), te_dev[l], L.emb.p, h->bf16(), n_t, HW, C, st));
-    GemmDesc a = gd();
-    a.A = L.emb.p; a.lda = 2 * C; a.W = L.w1; a.ldw = 2 * C; a.bias = L.b1; a.out = L.h1.p; a.ldo = (long long)L.nb * 4 * C;
-    a.M = Mt; a.N = L.nb * 4 * C; a.K = 2 * C; a.epi = EPI_STORE; a.act = ACT_RELU;
-    if ((rc = gemm(h, a, st, PK_ENC))) return rc;
-    GemmDesc b = gd();
-    b.A = L.h1.p; b.lda = (long long)L.nb * 4 * C; b.W = L.w2; b.ldw = 4 * C; b.bias = L.b2; b.out = L.film.p; b.ldo = 2 * C;
-    b.M = Mt; b.N = 2 * C; b.K = 4 * C; b.epi = EPI_STORE_F32;
-    b.batch = L.nb; b.a_koff_b = 4 * C; b.w_row_b = 2 * C; b.out_off_b = (long long)Mt * 2 * C; b.bias_off_b = 2 * C;
-    if ((rc = gemm(h, b, st, PK_ENC))) return rc;
-  }
+  if (!pre)
+    for (int l = 0; l < S; ++l)
+      if ((rc = issue_encodings(h, l, (Hs >> l) * (Ws >> l), n_t, te_dev[l], st))) return rc;
   // ---- encoder_first (unet.py:90)
   CKLP(PK_EDGE, 0, launch_stem(u.sp_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
                   cfg.channels[0], st));
@@ -747,7 +756,8 @@ extern "C" int ldmb_set_use_graphs(ldmb_handle* h, int on) {
 extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
                                  const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
                                  const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
-  if (!h || !x_dev || !out_dev || !t_index || !te_host || !plan) return LDMB_ERR_INVALID;
+  if (!h || !x_dev || !out_dev || !t_index || !plan) return LDMB_ERR_INVALID;
+  const bool pre = te_host == nullptr;      // FiLM tables of the n_t timesteps were precomputed (ldmb_unet_precompute_film)
   UNetState& u = h->unet;
   if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
   if (!u.missing.empty())
@@ -762,6 +772,9 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   if ((Hs % (1 << (S - 1))) || (Ws % (1 << (S - 1))))
     return fail(h, LDMB_ERR_INVALID, "resolution %dx%d is not divisible by 2^%d: skip shapes would not match (unet.py:101)", Hs, Ws, S - 1);
   for (int b = 0; b < B; ++b) if (t_index[b] < 0 || t_index[b] >= n_t) return fail(h, LDMB_ERR_INVALID, "t_index out of range");
+  if (pre && (u.film_nt != n_t || u.film_Hs != Hs || u.film_Ws != Ws))
+    return fail(h, LDMB_ERR_STATE, "te_host == NULL needs ldmb_unet_precompute_film for %d timesteps at this resolution", n_t);
+  if (!pre) u.film_nt = 0;                   // this call overwrites the FiLM workspace
   for (int b = 0; b < nblk; ++b)
     if (!plan[3 * b] && (plan[3 * b + 1] < 0 || plan[3 * b + 1] >= kExperts || plan[3 * b + 2] < 0 || plan[3 * b + 2] >= kExperts))
       return fail(h, LDMB_ERR_INVALID, "plan: expert index out of range");
@@ -778,7 +791,7 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   const size_t off_tidx = off_plan + al((size_t)nblk * 16);
   size_t off_te[LDMB_MAX_LEVELS];
   size_t total = off_tidx + al((size_t)B * 4);
-  for (int l = 0; l < S; ++l) { off_te[l] = total; total += al((size_t)n_t * u.levels[l].C * 4); }
+  for (int l = 0; l < S; ++l) { off_te[l] = total; total += pre ? 0 : al((size_t)n_t * u.levels[l].C * 4); }
   if ((rc = ensure(h, u.stepbuf, total))) return rc;
   char* sb = static_cast<char*>(u.stepbuf.p);
   u.sp_dev = reinterpret_cast<const StepParams*>(sb);
@@ -813,7 +826,7 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   int* hplan = reinterpret_cast<int*>(hp + off_plan);
   for (int b = 0; b < nblk; ++b) { hplan[4 * b] = plan[3 * b]; hplan[4 * b + 1] = plan[3 * b + 1]; hplan[4 * b + 2] = plan[3 * b + 2]; hplan[4 * b + 3] = 0; }
   memcpy(hp + off_tidx, t_index, (size_t)B * 4);
-  for (int l = 0; l < S; ++l) {
+  for (int l = 0; l < S && !pre; ++l) {
     if (!te_host[l]) return fail(h, LDMB_ERR_INVALID, "te_host[%d] is NULL", l);
     memcpy(hp + off_te[l], te_host[l], (size_t)n_t * u.levels[l].C * 4);
   }
@@ -827,10 +840,10 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   UNetState::GraphEntry* ge = nullptr;
   if (u.use_graphs && !h->prof_on && cap == cudaStreamCaptureStatusNone) {
     for (auto& g : u.graphs)
-      if (g.B == B && g.Hs == Hs && g.Ws == Ws && g.n_t == n_t) { ge = &g; break; }
+      if (g.B == B && g.Hs == Hs && g.Ws == Ws && g.n_t == n_t && g.pre == (int)pre) { ge = &g; break; }
     if (!ge) {
       if (u.graphs.size() >= 16) { for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec); u.graphs.clear(); }
-      u.graphs.push_back({B, Hs, Ws, n_t, u.ws_epoch, nullptr, 0, 0});
+      u.graphs.push_back({B, Hs, Ws, n_t, (int)pre, u.ws_epoch, nullptr, 0, 0});
       ge = &u.graphs.back();
     }
     if (ge->epoch != u.ws_epoch) {     // a workspace moved since capture: the graph holds stale pointers
@@ -847,7 +860,7 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
     const long long l0 = h->launches;
     if (!u.cap_stream) CK(cudaStreamCreateWithFlags(&u.cap_stream, cudaStreamNonBlocking));
     CK(cudaStreamBeginCapture(u.cap_stream, cudaStreamCaptureModeThreadLocal));
-    rc = issue_forward(h, B, Hs, Ws, n_t, te_dev, u.cap_stream);
+    rc = issue_forward(h, B, Hs, Ws, n_t, te_dev, u.cap_stream, pre);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(u.cap_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -860,7 +873,40 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
     return LDMB_OK;
   }
   if (ge) ge->seen++;
-  return issue_forward(h, B, Hs, Ws, n_t, te_dev, st);
+  return issue_forward(h, B, Hs, Ws, n_t, te_dev, st, pre);
+}
+
+extern "C" int ldmb_unet_precompute_film(ldmb_handle* h, int H, int W, int n_t, const float* const* te_host, void* stream) {
+  if (!h || !te_host || n_t < 1) return LDMB_ERR_INVALID;
+  UNetState& u = h->unet;
+  if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
+  if (!u.missing.empty())
+    return fail(h, LDMB_ERR_STATE, "%d UNet parameters not loaded (first: %s)", (int)u.missing.size(), u.missing.begin()->c_str());
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = u.cfg.num_levels, s = u.cfg.stem_size;
+  if (H < s || W < s || H % s || W % s) return fail(h, LDMB_ERR_INVALID, "precompute: bad resolution");
+  const int Hs = H / s, Ws = W / s;
+  if ((Hs % (1 << (S - 1))) || (Ws % (1 << (S - 1)))) return fail(h, LDMB_ERR_INVALID, "resolution %dx%d is not divisible by 2^%d", Hs, Ws, S - 1);
+  for (int l = 0; l < S; ++l)
+    if (u.levels[l].peH != (Hs >> l) || u.levels[l].peW != (Ws >> l) || !u.levels[l].pe.p)
+      return fail(h, LDMB_ERR_STATE, "position table of level %d not set for %dx%d", l, Hs >> l, Ws >> l);
+  int rc;
+  u.film_nt = 0;
+  if ((rc = unet_reserve(h, 1, Hs, Ws, n_t))) return rc;
+  size_t off[LDMB_MAX_LEVELS], total = 0;
+  for (int l = 0; l < S; ++l) { off[l] = total; total += ((size_t)n_t * u.levels[l].C * 4 + 255) & ~size_t(255); }
+  if ((rc = ensure(h, u.te_pre, total))) return rc;
+  for (int l = 0; l < S; ++l) {
+    if (!te_host[l]) return fail(h, LDMB_ERR_INVALID, "te_host[%d] is NULL", l);
+    CK(cudaMemcpyAsync(static_cast<char*>(u.te_pre.p) + off[l], te_host[l], (size_t)n_t * u.levels[l].C * 4, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaStreamSynchronize(st));            // the host tables may go away when we return (one-off per schedule)
+  for (int l = 0; l < S; ++l)
+    if ((rc = issue_encodings(h, l, (Hs >> l) * (Ws >> l), n_t, reinterpret_cast<const float*>(static_cast<char*>(u.te_pre.p) + off[l]), st)))
+      return rc;
+  u.film_nt = n_t; u.film_Hs = Hs; u.film_Ws = Ws;
+  return LDMB_OK;
 }
 
 // =====================================================================================

@@ -94,8 +94,12 @@ class DDPM(nn.Module):
         fused = isinstance(self.model, UNet)
         bar = tqdm(total=len(pairs), disable=not progress)
         first = True
-        for t, t_next in pairs:
+        chunk = self.model.film_chunk(x.shape[2] // self.model.stem_size, x.shape[3] // self.model.stem_size) if fused else 0
+        for i, (t, t_next) in enumerate(pairs):
             t, t_next = int(t), int(t_next)
+            if fused and i % chunk == 0:
+                # the batch-invariant Encodings MLP of the next `chunk` steps in one batched pass
+                self.model.precompute_film(x, [int(p[0]) for p in pairs[i:i + chunk]])
             co, sigma = self.ddim_scalars(alpha_cum, t, t_next, eta)
             if fused:
                 # ddpm.py:78 then :80 -- the noise is drawn every step (even for eta=0) so the torch

@@ -150,12 +150,19 @@ class Handle:
         Cc, Hl, Wl = pe.shape
         self.check(self.lib.ldmb_unet_set_position_table(self.h, level, pe.data_ptr(), Cc, Hl, Wl, stream_ptr(self.device)))
 
+    def unet_precompute_film(self, H: int, W: int, te_tables: Sequence[torch.Tensor]) -> None:
+        te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
+        self.check(self.lib.ldmb_unet_precompute_film(self.h, H, W, te_tables[0].shape[0], te_ptrs, stream_ptr(self.device)))
+
     def unet_forward(self, x: torch.Tensor, out: torch.Tensor, t_index, te_tables: Sequence[torch.Tensor], plan,
                      coef: Optional[_lib.DdimCoef] = None, noise: Optional[torch.Tensor] = None) -> None:
         B, _, H, W = x.shape
-        n_t = te_tables[0].shape[0]
+        if isinstance(te_tables, int):       # FiLM tables precomputed for this many timesteps (unet_precompute_film)
+            n_t, te_ptrs = te_tables, None
+        else:
+            n_t = te_tables[0].shape[0]
+            te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
         ti = (C.c_int32 * B)(*t_index)
-        te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
         flat = [int(v) for row in plan for v in row]
         pl = (C.c_int32 * len(flat))(*flat)
         self.check(self.lib.ldmb_unet_forward(

@@ -91,6 +91,7 @@ class UNet(nn.Module):
         self.precision = runtime.default_precision()
         self._handle: Optional[runtime.Handle] = None
         self._pe_res = None
+        self._film = None      # (handle, (H, W), {t: row}) of the FiLM tables precomputed for a schedule
 
     # ------------------------------------------------------------------ host-side helpers
     def set_precision(self, precision: str) -> "UNet":
@@ -98,7 +99,7 @@ class UNet(nn.Module):
         if precision not in runtime.PRECISIONS:
             raise ValueError(precision)
         if precision != self.precision:
-            self.precision, self._handle, self._pe_res = precision, None, None
+            self.precision, self._handle, self._pe_res, self._film = precision, None, None, None
         return self
 
     def blocks_in_execution_order(self) -> List[SwinBlock]:
@@ -128,14 +129,43 @@ class UNet(nn.Module):
         if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
             h = runtime.Handle(device, self.precision)
             h.unet_configure(self.input_channels, self.stage_blocks, self.stage_channels, self.stem_size)
-            self._handle, self._pe_res = h, None
+            self._handle, self._pe_res, self._film = h, None, None
             check_params = True
         if check_params:
             items = self.__dict__.get("_param_items")
             if items is None:      # (name, tensor) pairs; dropped whenever the module tree may have new tensors
                 items = self.__dict__["_param_items"] = list(self.state_dict(keep_vars=True).items())
-            h.unet_load(items)
+            if h.unet_load(items):
+                self._film = None      # precomputed FiLM tables are stale
         return h
+
+    def _set_position_tables(self, h: runtime.Handle, Hs: int, Ws: int) -> None:
+        if self._pe_res != (Hs, Ws):
+            for lvl, c in enumerate(self.stage_channels):
+                h.unet_set_position_table(lvl, self.encoder_stages[lvl].stage.blocks[0].encodings.pe.table(Hs >> lvl, Ws >> lvl))
+            self._pe_res = (Hs, Ws)
+            self._film = None
+
+    FILM_BYTES_BUDGET = 3 << 30       # device memory for the per-schedule FiLM tables + their scratch
+
+    def film_chunk(self, Hs: int, Ws: int) -> int:
+        """How many timesteps of FiLM tables fit the budget (tables fp32 [blocks][t][HW][2C] + bf16 scratch of equal size)."""
+        per_t = 0
+        for lvl, (n, c) in enumerate(zip(self.stage_blocks, self.stage_channels)):
+            per_t += 2 * n * (Hs >> lvl) * (Ws >> lvl) * 2 * c * (4 + 4)
+        return max(1, self.FILM_BYTES_BUDGET // max(per_t, 1))
+
+    def precompute_film(self, x: torch.Tensor, timesteps: Sequence[int]) -> None:
+        """Evaluate the Encodings MLP (unet.py:18-21) of every block for all `timesteps` at x's resolution in one
+        batched pass; denoise steps at these timesteps then skip it (it depends on (t, h, w) only)."""
+        runtime._require_cuda(x, "UNet input")
+        with torch.cuda.device(x.device):
+            h = self._prepare(x.device, True)
+            H, W = x.shape[2], x.shape[3]
+            self._set_position_tables(h, H // self.stem_size, W // self.stem_size)
+            uniq = sorted(set(int(t) for t in timesteps))
+            h.unet_precompute_film(H, W, self._time_tables(uniq))
+            self._film = (h, (H, W), {t: i for i, t in enumerate(uniq)})
 
     def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float(): tensors may be replaced
         self.__dict__.pop("_param_items", None)
@@ -171,13 +201,15 @@ class UNet(nn.Module):
             h = self._prepare(x.device, check_params)
             B, _, H, W = x.shape
             Hs, Ws = H // self.stem_size, W // self.stem_size
-            if self._pe_res != (Hs, Ws):
-                for lvl, c in enumerate(self.stage_channels):
-                    h.unet_set_position_table(lvl, self.encoder_stages[lvl].stage.blocks[0].encodings.pe.table(Hs >> lvl, Ws >> lvl))
-                self._pe_res = (Hs, Ws)
-            uniq = sorted(set(int(v) for v in t_values))
-            index = {v: i for i, v in enumerate(uniq)}
-            te = self._time_tables(uniq)
+            self._set_position_tables(h, Hs, Ws)
+            film = self._film
+            if film is not None and film[0] is h and film[1] == (H, W) and all(int(v) in film[2] for v in t_values):
+                index, te = film[2], len(film[2])           # FiLM tables of these timesteps are already on the device
+            else:
+                self._film = None                           # this call overwrites the FiLM workspace
+                uniq = sorted(set(int(v) for v in t_values))
+                index = {v: i for i, v in enumerate(uniq)}
+                te = self._time_tables(uniq)
             if plan is None:
                 plan = self.draw_plan()
             if out is None:

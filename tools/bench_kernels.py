@@ -53,7 +53,11 @@ def main():
         us = timeit(lambda i: h.gemm(A[i % NB], W[i % NB], bias, out[i % NB], M, N, K))
         fl = 2.0 * M * N * K
         by = 2.0 * (M * K + N * K + M * N)
-        print(f"gemm {name:8s} M={M:6d} N={N:5d} K={K:5d}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s(alg)")
+        lib = ""
+        if os.environ.get("CUBLAS"):       # library reference point for the same shape (plain bf16 GEMM, no epilogue)
+            us2 = timeit(lambda i: torch.matmul(A[i % NB], W[i % NB].t(), out=out[i % NB]))
+            lib = f"   | cuBLAS {us2:7.1f} us {fl / us2 / 1e6:7.1f} TFLOP/s"
+        print(f"gemm {name:8s} M={M:6d} N={N:5d} K={K:5d}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s(alg){lib}")
     if only:
         return
     convs = [(B, 32, 32, 512, 512), (B, 64, 64, 256, 256), (B, 128, 128, 128, 128), (B, 256, 256, 64, 64)]

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Where does the time go inside one tcgen05 GEMM launch?  Per-CTA %globaltimer stamps (debug hook)."""
 import ctypes as C
+import ctypes as C_
 import os
 import sys
 
@@ -13,8 +14,34 @@ from ldm_image_generator_b200 import runtime  # noqa: E402
 NAMES = ["entry", "setup", "prev_done", "tma0", "data0", "mma_end", "acc0", "accN", "epi_end", "exit"]
 
 
+def gconv(h, lvl):
+    B, C, H = 64, 128 << lvl, 32 >> lvl
+    xm = torch.randn(B, H, H, C, device="cuda").bfloat16(); x = torch.randn(B, H, H, C, device="cuda")
+    w = torch.randn(C, 576, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda")
+    for _ in range(3):
+        h.grouped_conv3x3(xm, w, b, x, B, H, H, C)
+    torch.cuda.synchronize()
+    h.lib.ldmb_debug_tc_trace(h.h, 1, None, 0)
+    for _ in range(4):
+        h.grouped_conv3x3(xm, w, b, x, B, H, H, C)
+    buf = (C_.c_int64 * (16 * 256))()
+    h.lib.ldmb_debug_tc_trace(h.h, 1, buf, 256)
+    h.lib.ldmb_debug_tc_trace(h.h, 0, None, 0)
+    a = np.frombuffer(buf, dtype=np.int64).reshape(256, 16)[:148, :11].astype(np.float64)
+    a = a[a[:, 0] > 0]
+    rel = (a - a[:, 0].min()) / 1000.0
+    print(f"gconv level {lvl}: {len(a)} CTAs, kernel span {rel[:, 9].max():.2f} us")
+    for i, nm in enumerate(NAMES + ["weights"]):
+        col = rel[:, i]
+        print(f"   {nm:10s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f} us")
+
+
 def main():
     h = runtime.Handle(torch.device("cuda", 0), "bf16")
+    if len(sys.argv) > 2 and sys.argv[1] == "gconv":
+        for lvl in sys.argv[2:]:
+            gconv(h, int(lvl))
+        return
     shapes = [(4096, 1536, 512), (4096, 3072, 512), (65536, 768, 128), (4096, 512, 1536), (1024, 6144, 1024), (16384, 1536, 256)]
     if len(sys.argv) > 3:
         shapes = [tuple(int(v) for v in sys.argv[1:4])]
