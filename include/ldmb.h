@@ -115,7 +115,7 @@ int ldmb_debug_tc_trace(ldmb_handle* h, int enable, int64_t* stamps_host, int ma
 /* Per-kernel-class device timing for roofline reports (bench.py).  Between begin and end every launch is
  * bracketed by CUDA events on its stream; end synchronises and returns, per class, the summed event time (ms),
  * the summed algorithmic work (FLOPs for the GEMM/conv classes, bytes for the HBM-bound ones) and the launch count.
- * Classes (tcgen05 unless noted): 0 ReGLU a|b GEMM, 1 ReGLU c (+ attention out_proj) GEMM into the residual stream,
+ * Classes (tcgen05 unless noted): 0 ReGLU a|b GEMM (C = 128/256: the fused a|b -> gate -> c kernel), 1 ReGLU c (+ attention out_proj) GEMM into the residual stream,
  * 2 attention in_proj GEMM, 3 hoisted Encodings MLP GEMMs, 4 level-change 1x1 convs, 5 grouped 3x3 conv,
  * 6 VAE dense 3x3 conv, 7 VAE ConvTranspose / 1x1 GEMMs, 8 CUDA-core GEMM/conv (fp32 validation mode, toy widths),
  * 9 ChannelNorm+FiLM, 10 window attention core, 11 stem + final (decoder_last + DDIM update), 12 other.
@@ -209,6 +209,13 @@ int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const
  * implicit-GEMM kernel instead of the halo-patch kernel. */
 int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* w_packed, const float* bias, float* x, int B,
                          int H, int W, int C, int force_generic, void* stream);
+
+/* RandomMoE of ReGLU experts (modules.py:14-15,34-36) as one fused kernel, bf16 mode, C = 128 or 256:
+ * x fp32 [M,C] += sum over {general, experts e1, e2} of c_e(a_e(xm) * relu(b_e(xm))).
+ * w_ab [5*2C, C]: per expert block (general first) the rows of a and b interleaved in chunks of 64 (64 a rows, 64 b rows, ...),
+ * b_ab fp32 [5*2C] alike; w_c [5*C, C] (row = expert*C + output channel), b_c fp32 [5*C]. */
+int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                   float* x, int M, int C, int e1, int e2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,13 @@ bool gconv_halo_supported(int B, int H, int W, int C);
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
                               int C, const int* plan, cudaStream_t st);
 
+// Fused ReGLU feed-forward (kernels_mlp.cu), C = 128 / 256: x fp32 [M,C] += sum over {general, e1, e2} of
+// c_e(a_e(xm) * relu(b_e(xm))).  Weight layouts as in the two-GEMM path (w_ab [5*2C, C] a|b interleaved in chunks of 64,
+// w_c [w_c_rows >= 5C, C]).  plan: {skip, e1, e2, -} on the device, or NULL to use e1 / e2.
+bool mlp_fused_supported(int M, int C);
+cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                             float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, cudaStream_t st);
+
 // ---- weight repack: dst[T] (4-d, dst strides) = src[fp32] (4-d, src strides)
 cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int dims[4],
                           const long long sstr[4], const long long dstr[4], cudaStream_t s);

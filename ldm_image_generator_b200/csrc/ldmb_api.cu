@@ -657,6 +657,18 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
                                  global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, pl, st));
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
+  if (h->bf16() && !h->force_simt && mlp_fused_supported(M, C)) {
+    // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM
+    CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
+         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, st));
+    if (w.attn) {   // x += att . W_out^T + b_out   (attention.py:82 out_proj; unet.py:44,47)
+      GemmDesc c = gd();
+      c.A = toff(h, u.hbuf.p, 3LL * C); c.lda = ldh; c.W = toff(h, w.w_c, 5LL * C * C); c.ldw = C; c.bias = w.b_c + 5LL * C;
+      c.out = x; c.ldo = C; c.M = M; c.N = C; c.K = C; c.epi = EPI_ACCUM_F32; c.plan = pl;
+      if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
+    }
+    return LDMB_OK;
+  }
   {
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
@@ -1214,4 +1226,15 @@ extern "C" int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* 
   if (!h || !xm || !w_packed || !bias || !x || B < 1 || H < 1 || W < 1 || C < kHeadDim || C % kHeadDim) return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   return grouped_conv(h, xm, w_packed, bias, x, B, H, W, C, nullptr, static_cast<cudaStream_t>(stream), force_generic != 0);
+}
+
+extern "C" int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                              float* x, int M, int C, int e1, int e2, void* stream) {
+  if (!h || !xm || !w_ab || !b_ab || !w_c || !b_c || !x || M < 1 || e1 < 0 || e1 >= kExperts || e2 < 0 || e2 >= kExperts)
+    return LDMB_ERR_INVALID;
+  if (!h->bf16() || !mlp_fused_supported(M, C)) return fail(h, LDMB_ERR_UNSUPPORTED, "fused feed-forward: bf16 mode, C = 128 or 256");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, st));
+  return LDMB_OK;
 }

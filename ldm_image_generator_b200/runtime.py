@@ -203,6 +203,10 @@ class Handle:
         self.check(self.lib.ldmb_conv3x3(self.h, x.data_ptr(), Wt.data_ptr(), bias.data_ptr() if bias is not None else None,
                                          out.data_ptr(), B, H, W, Cc, N, act, int(force_simt), stream_ptr(self.device)))
 
+    def mlp_fused(self, xm, w_ab, b_ab, w_c, b_c, x, M, Cc, e1, e2) -> None:
+        self.check(self.lib.ldmb_mlp_fused(self.h, xm.data_ptr(), w_ab.data_ptr(), b_ab.data_ptr(), w_c.data_ptr(), b_c.data_ptr(),
+                                           x.data_ptr(), M, Cc, e1, e2, stream_ptr(self.device)))
+
     def grouped_conv3x3(self, xm, w_packed, bias, x, B, H, W, Cc, force_generic=False) -> None:
         self.check(self.lib.ldmb_grouped_conv3x3(self.h, xm.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), x.data_ptr(),
                                                  B, H, W, Cc, int(force_generic), stream_ptr(self.device)))

@@ -178,3 +178,28 @@ def test_grouped_conv3x3_accumulates_into_residual(handles, B, H, W, C, generic)
     ref = F.conv2d(xm.float().permute(0, 3, 1, 2), w.float(), b, padding=1, groups=C // 32).permute(0, 2, 3, 1)
     assert h.device_fault() == 0
     assert _rel(x - x0, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,C,e1,e2", [(256, 128, 0, 1), (4096, 128, 3, 2), (1000, 128, 1, 3), (65536, 128, 2, 0), (512, 256, 0, 3),
+                                       (16384, 256, 3, 1), (700, 256, 2, 1)])
+def test_mlp_fused_kernel(handles, M, C, e1, e2):
+    """Fused ReGLU feed-forward (general + 2 picked experts) vs fp64 torch on the same bf16-rounded operands."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(M + C + e1 * 5 + e2)
+    xm = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    wa = (torch.randn(5, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    wb = (torch.randn(5, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    wc = (torch.randn(5, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    ba, bb, bc = (torch.randn(5, C, device="cuda", generator=g) * 0.3 for _ in range(3))
+    # a|b rows interleaved in chunks of 64 per expert (ldmb.h)
+    w_ab = torch.stack([wa.reshape(5, C // 64, 64, C), wb.reshape(5, C // 64, 64, C)], dim=2).reshape(5 * 2 * C, C).contiguous()
+    b_ab = torch.stack([ba.reshape(5, C // 64, 64), bb.reshape(5, C // 64, 64)], dim=2).reshape(5 * 2 * C).contiguous()
+    x0 = torch.randn(M, C, device="cuda", generator=g)
+    x = x0.clone()
+    h.mlp_fused(xm, w_ab, b_ab, wc.reshape(5 * C, C).contiguous(), bc.reshape(5 * C).contiguous(), x, M, C, e1, e2)
+    ref = torch.zeros(M, C, device="cuda", dtype=torch.float64)
+    for e in (0, 1 + e1, 1 + e2):
+        hh = (xm.double() @ wa[e].double().t() + ba[e].double()) * torch.relu(xm.double() @ wb[e].double().t() + bb[e].double())
+        ref += hh.bfloat16().double() @ wc[e].double().t() + bc[e].double()       # h is rounded to bf16 between the two GEMMs
+    assert h.device_fault() == 0
+    assert _rel(x - x0, ref) < 2e-3

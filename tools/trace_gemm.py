@@ -36,8 +36,40 @@ def gconv(h, lvl):
         print(f"   {nm:10s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f} us")
 
 
+def mlp(h, lvl):
+    Cc, M = 128 << lvl, 65536 >> (2 * lvl)
+    xm = torch.randn(M, Cc, device="cuda").bfloat16(); x = torch.randn(M, Cc, device="cuda")
+    w_ab = torch.randn(10 * Cc, Cc, device="cuda").bfloat16(); w_c = torch.randn(5 * Cc, Cc, device="cuda").bfloat16()
+    b_ab = torch.zeros(10 * Cc, device="cuda"); b_c = torch.zeros(5 * Cc, device="cuda")
+    for _ in range(3):
+        h.mlp_fused(xm, w_ab, b_ab, w_c, b_c, x, M, Cc, 1, 2)
+    torch.cuda.synchronize()
+    h.lib.ldmb_debug_tc_trace(h.h, 1, None, 0)
+    for _ in range(4):
+        h.mlp_fused(xm, w_ab, b_ab, w_c, b_c, x, M, Cc, 1, 2)
+    buf = (C_.c_int64 * (16 * 256))()
+    h.lib.ldmb_debug_tc_trace(h.h, 1, buf, 256)
+    h.lib.ldmb_debug_tc_trace(h.h, 0, None, 0)
+    raw = np.frombuffer(buf, dtype=np.int64).reshape(256, 16)[:148].astype(np.float64)
+    raw = raw[raw[:, 0] > 0]
+    rel = (raw[:, :10] - raw[:, 0].min()) / 1000.0
+    print(f"mlp_fused level {lvl} (C={Cc}, M={M}): {len(raw)} CTAs, kernel span {rel[:, 9].max():.2f} us")
+    for i, nm in enumerate(["entry", "setup", "prev_done", "a1_landed", "mma_tile0", "mma_end", "epi_first", "epi_tile0", "epi_end", "exit"]):
+        col = rel[:, i][raw[:, i] > 0]
+        if len(col):
+            print(f"   {nm:10s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f} us")
+    lead = raw[raw[:, 5] > 0]
+    for i, nm in enumerate(["h_full", "b1_full", "b2_full", "d1_empty", "d2_empty+a1_full", "(commit issue)"]):
+        col = lead[:, 10 + i] / 1965.0
+        print(f"   MMA thread waited on {nm:9s} median {np.median(col):7.2f} us  max {col.max():7.2f} us")
+
+
 def main():
     h = runtime.Handle(torch.device("cuda", 0), "bf16")
+    if len(sys.argv) > 2 and sys.argv[1] == "mlp":
+        for lvl in sys.argv[2:]:
+            mlp(h, int(lvl))
+        return
     if len(sys.argv) > 2 and sys.argv[1] == "gconv":
         for lvl in sys.argv[2:]:
             gconv(h, int(lvl))
