@@ -591,13 +591,21 @@ __global__ void __launch_bounds__(256) final_warp_kernel(const float* __restrict
   float* __restrict__ out = co.out;
   const int lane = threadIdx.x & 31;
   const int J = Cin * s * s;
+  // weights [C0][J] -> shared [8][C0] (transposed, zero rows for j >= J) with coalesced loads, then 16-byte reads:
+  // loading the lane's slice straight from global costs 32 sectors per load instruction (stride J floats per lane)
+  __shared__ __align__(16) float wsh[8 * 128 * V];
+  for (int i = threadIdx.x; i < 8 * 128 * V; i += blockDim.x) wsh[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128 * V * J; i += blockDim.x) wsh[(i % J) * (128 * V) + i / J] = w[i];
+  __syncthreads();
   float wr[8][4 * V];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int i = 0; i < V; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) wr[j][4 * i + e] = j < J ? w[(long long)(i * 128 + lane * 4 + e) * J + j] : 0.f;
+    for (int i = 0; i < V; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(wsh + j * (128 * V) + i * 128 + lane * 4);
+      wr[j][4 * i] = t.x; wr[j][4 * i + 1] = t.y; wr[j][4 * i + 2] = t.z; wr[j][4 * i + 3] = t.w;
+    }
   // output owned by this lane after the fold: bit 4 -> +4, bit 3 -> +2, bit 2 -> +1
   const int jl = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const float bj = jl < J ? bias[jl / (s * s)] : 0.f;
@@ -698,6 +706,87 @@ __global__ void __launch_bounds__(256) pointwise_out_kernel(const T* __restrict_
     if (out_u8) {
       const float c = fminf(fmaxf(v, -1.f), 1.f);
       out_u8[m * Cout + j] = (uint8_t)(c * 127.5f + 127.5f);   // truncation, sample_ldm.py:77
+    }
+  }
+}
+
+// to_rgb-style few-output 1x1 conv out of an NHWC bf16 tensor, fast path (Cout <= 4, C a multiple of 64): G lanes
+// share a pixel (8 channels = one 16-byte load per lane per 8*G channels), partial dot products are folded with
+// log2(G) shuffle steps, the group's first lane adds the bilinear-upsampled running sum (vae.py:131) and writes
+// NCHW fp32 (+ the uint8 HWC image of sample_ldm.py:75-77).  Bytes per pixel: 2C in, 4*Cout (+ Cout) out.
+template <int G, int ITERS>
+__global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, const float* __restrict__ prev,
+                                                                 float* __restrict__ out, uint8_t* __restrict__ out_u8,
+                                                                 int B, int H, int W, int C, int Cout) {
+  pdl_wait();
+  constexpr int PPW = 32 / G;                              // pixels per warp per iteration
+  const int lane = threadIdx.x & 31, gl = lane % G, gp = lane / G;
+  const int M = B * H * W;
+  float wr[ITERS][4][8];                                   // [pass][j][8 channels]; C = ITERS * 8 * G
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[it][j][e] = j < Cout ? w[(long long)j * C + it * 8 * G + gl * 8 + e] : 0.f;
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  constexpr int UNR = 4;                                   // pixel groups per iteration: UNR*ITERS independent 16-byte loads in flight per lane
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (PPW * UNR); mb < M; mb += wpg * PPW * UNR) {
+    uint4 u[UNR][ITERS];
+#pragma unroll
+    for (int r = 0; r < UNR; ++r) {
+      const int m = mb + r * PPW + gp;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+        u[r][it] = m < M ? __ldg(reinterpret_cast<const uint4*>(x + (long long)m * C + it * 8 * G + gl * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < UNR; ++r) {
+      const int m = mb + r * PPW + gp;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const uint32_t w4[4] = {u[r][it].x, u[r][it].y, u[r][it].z, u[r][it].w};
+        float xv[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
+          xv[2 * k] = __low2float(h2); xv[2 * k + 1] = __high2float(h2);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[j] = fmaf(xv[e], wr[it][j][e], a[j]);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+      if (gl == 0 && m < M) {
+        const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j >= Cout) break;
+          float v = a[j] + bias[j];
+          if (prev) {
+            const int Hs = H / 2, Ws = W / 2;
+            const int i0 = hh >> 1, j0 = ww >> 1;
+            const int ia = (hh & 1) ? i0 : max(i0 - 1, 0), ib = (hh & 1) ? min(i0 + 1, Hs - 1) : i0;
+            const int ja = (ww & 1) ? j0 : max(j0 - 1, 0), jb = (ww & 1) ? min(j0 + 1, Ws - 1) : j0;
+            const float wa_h = (hh & 1) ? 0.75f : 0.25f, wa_w = (ww & 1) ? 0.75f : 0.25f;
+            const float* pp = prev + ((long long)b * Cout + j) * Hs * Ws;
+            const float top = wa_w * pp[ia * Ws + ja] + (1.f - wa_w) * pp[ia * Ws + jb];
+            const float bot = wa_w * pp[ib * Ws + ja] + (1.f - wa_w) * pp[ib * Ws + jb];
+            v += wa_h * top + (1.f - wa_h) * bot;
+          }
+          if (out) out[(((long long)b * Cout + j) * H + hh) * W + ww] = v;
+          if (out_u8) {
+            const float c = fminf(fmaxf(v, -1.f), 1.f);
+            out_u8[(long long)m * Cout + j] = (uint8_t)(c * 127.5f + 127.5f);   // truncation, sample_ldm.py:77
+          }
+        }
+      }
     }
   }
 }
@@ -862,6 +951,16 @@ cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* 
   if (Cout > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
   const unsigned grid = (unsigned)((M + 31) / 32);
+  if (is_bf16 && Cout <= 4 && (C == 64 || C == 128 || C == 256 || C == 512) && M < (1LL << 31)) {
+    const int G = C >= 256 ? 32 : C / 8;                   // lanes per pixel, 8 channels per lane per pass
+    const int g2 = grid_for((M * G + 3) / 4, 256, 148 * 8);
+    const bf16* xb = (const bf16*)x;
+    if (C == 512) launch_k((pointwise_out_warp_kernel<32, 2>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+    else if (C == 256) launch_k((pointwise_out_warp_kernel<32, 1>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+    else if (C == 128) launch_k((pointwise_out_warp_kernel<16, 1>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+    else launch_k((pointwise_out_warp_kernel<8, 1>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
+    return cudaGetLastError();
+  }
   if (is_bf16) launch_k((pointwise_out_kernel<bf16>), grid, 256, 0, st, (const bf16*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
   else launch_k((pointwise_out_kernel<float>), grid, 256, 0, st, (const float*)x, w, bias, prev, out, out_u8, B, H, W, C, Cout);
   return cudaGetLastError();
