@@ -238,8 +238,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dom = max((k for k in kernels if kernels[k]["achieved"] is not None), key=lambda k: kernels[k]["ms"])
     tensor = kernels[dom]["unit"] == "TFLOP/s"
     peak = pk["tf_sustained"] if tensor else pk["hbm"]
+    # DRAM traffic of the dominant class's most frequent launch, from the committed `ncu --set full` capture
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(dom)
+        if t:
+            traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
     roofline = {"kernel": dom, "bound": "tensor" if tensor else "hbm", "achieved": kernels[dom]["achieved"], "peak": peak,
-                "unit": kernels[dom]["unit"], "frac": round(kernels[dom]["achieved"] / peak, 4), "traffic": None,
+                "unit": kernels[dom]["unit"], "frac": round(kernels[dom]["achieved"] / peak, 4), "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": pk["source"] + (", sustained (kernel timed inside a long step)" if tensor else ""),
                 "avg_launch_us": round(1000.0 * kernels[dom]["ms"] / kernels[dom]["launches"], 2)}
 

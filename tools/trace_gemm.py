@@ -75,18 +75,20 @@ def main():
             gconv(h, int(lvl))
         return
     shapes = [(4096, 1536, 512), (4096, 3072, 512), (65536, 768, 128), (4096, 512, 1536), (1024, 6144, 1024), (16384, 1536, 256)]
+    mode = 0
     if len(sys.argv) > 3:
         shapes = [tuple(int(v) for v in sys.argv[1:4])]
+        mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0     # 0 bf16 store, 2 fp32 accumulate (split-K path)
     for (M, N, K) in shapes:
         A = torch.randn(M, K, device="cuda").bfloat16(); W = torch.randn(N, K, device="cuda").bfloat16()
-        bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=torch.float32 if mode else torch.bfloat16)
         for _ in range(3):
-            h.gemm(A, W, bias, out, M, N, K)
+            h.gemm(A, W, bias, out, M, N, K, out_f32=mode)
         torch.cuda.synchronize()
         h.lib.ldmb_debug_tc_trace(h.h, 1, None, 0)
         # back-to-back launches so the traced one sees a busy predecessor
         for _ in range(4):
-            h.gemm(A, W, bias, out, M, N, K)
+            h.gemm(A, W, bias, out, M, N, K, out_f32=mode)
         buf = (C.c_int64 * (16 * 256))()
         n = h.lib.ldmb_debug_tc_trace(h.h, 1, buf, 256)
         h.lib.ldmb_debug_tc_trace(h.h, 0, None, 0)
