@@ -141,7 +141,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d_tmem = tmem_base + as * kSlice;
 #pragma unroll 1
         for (int tap = 0; tap < ((g.dbg & 2) ? 1 : 9); ++tap) {
-          const uint32_t a_addr = a_base + ((tap / 3) * g.pitch + tap % 3) * 128;
+          const uint32_t a_addr = a_base + ((g.dbg & 4) ? (tap / 3) * 8 : ((tap / 3) * g.pitch + tap % 3)) * 128;   // dbg 4: 8-row aligned offsets (wrong results)
           const uint32_t w_addr = w_base + tap * kWTile;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -200,6 +200,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 128);
   if (threadIdx.x == 0) trace_stamp(trace, 9);
 }
+
 
 }  // namespace
 
