@@ -120,6 +120,11 @@ def build_cpu_arm():
 def run_reference(args, rank: int):
     if rank != 0:
         return
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     R, sd_u, ucfg, sd_d, dcfg = build_cpu_arm()
     random.seed(0); torch.manual_seed(0)
     ub = 4
@@ -271,6 +276,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                            "achieved_tflops_per_gpu": round(alg_tflop / (ms / args.steps * 1e-3), 1),
                            "frac_of_sustained_bf16_peak": round(alg_tflop / (ms / args.steps * 1e-3) / pk["tf_sustained"], 4)}}
     if world == 1 and not args.no_cpu_baseline:
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except Exception:
+            pass
         R, sd_u, ucfg, sd_d, dcfg = build_cpu_arm()
         cpu_sample_once(sd_u, ucfg, sd_d, dcfg, R, args.num_steps, 4, L)
         t0, vals = time.perf_counter(), []
