@@ -31,6 +31,12 @@ bool mlp_fused_supported(int M, int C);
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, cudaStream_t st);
 
+// Dense 3x3 conv with 64 input and 64 output channels through the same halo-patch kernel (VAE level at full resolution):
+// out bf16 [B,H,W,64] = act(conv(in) + bias) (+ res), act(v) = max(v,0) + slope*min(v,0); w [64][9*64] tap-major.
+bool conv64_halo_supported(int C, int N);
+cudaError_t launch_conv64_halo(TcContext* ctx, const void* in, const void* w, const float* bias, void* out, const void* res, int B,
+                               int H, int W, float slope, cudaStream_t st);
+
 // ---- weight repack: dst[T] (4-d, dst strides) = src[fp32] (4-d, src strides)
 cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int dims[4],
                           const long long sstr[4], const long long dstr[4], cudaStream_t s);

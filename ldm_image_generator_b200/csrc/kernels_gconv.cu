@@ -35,6 +35,8 @@ struct GconvGeom {
   int w_tiles, h_tiles, b_tiles;           // spatial tiling
   int a_bytes, stage_bytes, stages;
   int dbg;                                 // debug experiments: 1 = no reds, 2 = one tap only
+  // dense mode (VAE 3x3 conv with 64 input and 64 output channels, vae.py:57-58): out(bf16) = act(acc + bias) (+ res)
+  int dense; float slope; bf16* out; const bf16* res;
 };
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
@@ -168,7 +170,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int wt = sp % g.w_tiles, ht = (sp / g.w_tiles) % g.h_tiles, bt = sp / (g.w_tiles * g.h_tiles);
       const int b = bt * g.TB + img, hh = ht * g.TH + yy, ww = wt * g.TW + xx;
       const bool valid = img < g.TB && b < g.B && yy < g.TH && hh < g.H && xx < g.TW && ww < g.W;
-      float* orow = x + (((long long)b * g.H + hh) * g.W + ww) * g.C + z * kSlice;
+      const long long pix = (((long long)b * g.H + hh) * g.W + ww) * g.C + z * kSlice;
+      float* orow = x + pix;
       if (!wait_bar(&tfull[as], aphase, s_abort, fault, 15)) break;
       if (threadIdx.x == 64) trace_stamp(trace, sp == sp0 ? 6 : 7);
       ptx::tc_fence_after();
@@ -178,7 +181,28 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_row + half * 32, v);
         ptx::tmem_ld_wait();
-        if (valid && !(g.dbg & 1)) {
+        if (valid && g.dense) {
+          // act(v) = max(v,0) + slope*min(v,0); one full 64-byte half row per thread
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + half * 32 + 4 * u));
+            float t0 = __uint_as_float(v[4 * u]) + bb.x, t1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+            float t2 = __uint_as_float(v[4 * u + 2]) + bb.z, t3 = __uint_as_float(v[4 * u + 3]) + bb.w;
+            t0 = fmaxf(t0, 0.f) + g.slope * fminf(t0, 0.f); t1 = fmaxf(t1, 0.f) + g.slope * fminf(t1, 0.f);
+            t2 = fmaxf(t2, 0.f) + g.slope * fminf(t2, 0.f); t3 = fmaxf(t3, 0.f) + g.slope * fminf(t3, 0.f);
+            if (g.res != nullptr) {
+              const uint2 rr = __ldg(reinterpret_cast<const uint2*>(g.res + pix + half * 32 + 4 * u));
+              const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rr.x), r23 = *reinterpret_cast<const __nv_bfloat162*>(&rr.y);
+              t0 += __low2float(r01); t1 += __high2float(r01); t2 += __low2float(r23); t3 += __high2float(r23);
+            }
+            __nv_bfloat162 p01 = __floats2bfloat162_rn(t0, t1), p23 = __floats2bfloat162_rn(t2, t3);
+            pk[2 * u] = *reinterpret_cast<uint32_t*>(&p01); pk[2 * u + 1] = *reinterpret_cast<uint32_t*>(&p23);
+          }
+          uint4* op = reinterpret_cast<uint4*>(g.out + pix + half * 32);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) op[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        } else if (valid && !(g.dbg & 1)) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + half * 32 + 4 * u));
@@ -211,12 +235,31 @@ bool gconv_halo_supported(int B, int H, int W, int C) {
 }
 
 // x fp32 [B,H,W,C] += conv3x3(xm bf16 [B,H,W,C], grouped by 32) + bias; w packed [C/64][64][9*64] block-diagonal pairs.
+static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
+                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res);
+
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
                               int C, const int* plan, cudaStream_t st) {
+  return launch_halo_common(ctx, xm, w, bias, x, B, H, W, C, plan, st, 0, 0.f, nullptr, nullptr);
+}
+
+bool conv64_halo_supported(int C, int N) { return g_gconv_mode != 0 && C == kSlice && N == kSlice; }
+
+// Dense 3x3 convolution with 64 input and 64 output channels (the highest-resolution VAE level, vae.py:57-58):
+// out bf16 [B,H,W,64] = act(conv(in) + bias) (+ res); w packed [64][9*64] tap-major -- the layout of one grouped-conv slice.
+cudaError_t launch_conv64_halo(TcContext* ctx, const void* in, const void* w, const float* bias, void* out, const void* res, int B,
+                               int H, int W, float slope, cudaStream_t st) {
+  return launch_halo_common(ctx, in, w, bias, nullptr, B, H, W, kSlice, nullptr, st, 1, slope, static_cast<bf16*>(out),
+                            static_cast<const bf16*>(res));
+}
+
+static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
+                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res) {
   GconvGeom g;
   memset(&g, 0, sizeof(g));
   g.B = B; g.H = H; g.W = W; g.C = C;
-  g.TW = W < 126 ? W : 126;
+  g.dense = dense; g.slope = slope; g.out = out; g.res = res;
+  g.TW = W < 128 ? W : 128;
   g.pitch = g.TW + 2;
   g.TH = (128 - g.TW) / g.pitch + 1;                       // largest TH with (TH-1)*pitch + TW <= 128
   g.TB = 1;

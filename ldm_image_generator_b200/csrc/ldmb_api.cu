@@ -1077,6 +1077,12 @@ int vae_reserve(ldmb_handle* h, int which, int B, int H0, int W0) {   // H0,W0: 
 // x -> ResBlock (vae.py:60-66): leaky(c2(leaky(c1(x)))) + x.  bufs: x in cur, scratch tmp, result in out.
 int res_block(ldmb_handle* h, const ResW& R, const void* x, void* tmp, void* out, int B, int Hl, int Wl, int C, cudaStream_t st) {
   int rc;
+  if (h->bf16() && !h->force_simt && conv64_halo_supported(C, C)) {   // C = 64: halo-patch kernel, every activation read once
+    const double fl = 2.0 * B * Hl * Wl * (double)C * 9 * C;
+    CKLP(PK_VAE_CONV, fl, launch_conv64_halo(h->tc, x, R.w1, R.b1, tmp, nullptr, B, Hl, Wl, kLeaky, st));
+    CKLP(PK_VAE_CONV, fl, launch_conv64_halo(h->tc, tmp, R.w2, R.b2, out, x, B, Hl, Wl, kLeaky, st));
+    return LDMB_OK;
+  }
   GemmDesc d = gd();
   d.A = x; d.lda = C; d.amode = AM_CONV3; d.cH = Hl; d.cW = Wl; d.cC = C; d.W = R.w1; d.ldw = 9LL * C; d.bias = R.b1;
   d.out = tmp; d.ldo = C; d.M = B * Hl * Wl; d.N = C; d.K = 9 * C; d.epi = EPI_STORE; d.act = ACT_LEAKY;
@@ -1194,6 +1200,12 @@ extern "C" int ldmb_conv3x3(ldmb_handle* h, const void* in, const void* W, const
                             int Wd, int C, int N, int act, int force_simt, void* stream) {
   if (!h || !in || !W || !out || B < 1 || H < 1 || Wd < 1 || C < 1 || N < 1) return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
+  if (h->bf16() && !h->force_simt && !force_simt && bias && conv64_halo_supported(C, N)) {
+    const float slope = act == ACT_RELU ? 0.f : (act == ACT_LEAKY ? kLeaky : 1.f);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CKLP(PK_VAE_CONV, 2.0 * B * H * Wd * (double)C * 9 * N, launch_conv64_halo(h->tc, in, W, bias, out, nullptr, B, H, Wd, slope, st));
+    return LDMB_OK;
+  }
   GemmDesc d = gd();
   d.A = in; d.lda = C; d.amode = AM_CONV3; d.cH = H; d.cW = Wd; d.cC = C; d.W = W; d.ldw = 9LL * C; d.bias = bias;
   d.out = out; d.ldo = N; d.M = B * H * Wd; d.N = N; d.K = 9 * C; d.epi = EPI_STORE; d.act = act;
