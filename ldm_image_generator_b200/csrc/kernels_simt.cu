@@ -763,28 +763,26 @@ __global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __r
       for (int o = G / 2; o > 0; o >>= 1)
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-      if (gl == 0 && m < M) {
+      // the butterfly leaves every lane of the group with all sums: lane gl finishes output channel j = gl
+      if (gl < Cout && m < M) {
+        const int j = gl;
         const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j >= Cout) break;
-          float v = a[j] + bias[j];
-          if (prev) {
-            const int Hs = H / 2, Ws = W / 2;
-            const int i0 = hh >> 1, j0 = ww >> 1;
-            const int ia = (hh & 1) ? i0 : max(i0 - 1, 0), ib = (hh & 1) ? min(i0 + 1, Hs - 1) : i0;
-            const int ja = (ww & 1) ? j0 : max(j0 - 1, 0), jb = (ww & 1) ? min(j0 + 1, Ws - 1) : j0;
-            const float wa_h = (hh & 1) ? 0.75f : 0.25f, wa_w = (ww & 1) ? 0.75f : 0.25f;
-            const float* pp = prev + ((long long)b * Cout + j) * Hs * Ws;
-            const float top = wa_w * pp[ia * Ws + ja] + (1.f - wa_w) * pp[ia * Ws + jb];
-            const float bot = wa_w * pp[ib * Ws + ja] + (1.f - wa_w) * pp[ib * Ws + jb];
-            v += wa_h * top + (1.f - wa_h) * bot;
-          }
-          if (out) out[(((long long)b * Cout + j) * H + hh) * W + ww] = v;
-          if (out_u8) {
-            const float c = fminf(fmaxf(v, -1.f), 1.f);
-            out_u8[(long long)m * Cout + j] = (uint8_t)(c * 127.5f + 127.5f);   // truncation, sample_ldm.py:77
-          }
+        float v = (j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]))) + bias[j];
+        if (prev) {
+          const int Hs = H / 2, Ws = W / 2;
+          const int i0 = hh >> 1, j0 = ww >> 1;
+          const int ia = (hh & 1) ? i0 : max(i0 - 1, 0), ib = (hh & 1) ? min(i0 + 1, Hs - 1) : i0;
+          const int ja = (ww & 1) ? j0 : max(j0 - 1, 0), jb = (ww & 1) ? min(j0 + 1, Ws - 1) : j0;
+          const float wa_h = (hh & 1) ? 0.75f : 0.25f, wa_w = (ww & 1) ? 0.75f : 0.25f;
+          const float* pp = prev + ((long long)b * Cout + j) * Hs * Ws;
+          const float top = wa_w * pp[ia * Ws + ja] + (1.f - wa_w) * pp[ia * Ws + jb];
+          const float bot = wa_w * pp[ib * Ws + ja] + (1.f - wa_w) * pp[ib * Ws + jb];
+          v += wa_h * top + (1.f - wa_h) * bot;
+        }
+        if (out) out[(((long long)b * Cout + j) * H + hh) * W + ww] = v;
+        if (out_u8) {
+          const float c = fminf(fmaxf(v, -1.f), 1.f);
+          out_u8[(long long)m * Cout + j] = (uint8_t)(c * 127.5f + 127.5f);   // truncation, sample_ldm.py:77
         }
       }
     }
