@@ -92,6 +92,11 @@ struct UNetState {
   unsigned long long ws_epoch = 0;     // bumped whenever a workspace is reallocated (cached graphs hold raw pointers)
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy NULL stream)
+  // The grouped conv of a block only needs xm and only adds into x: it runs on a side stream (a forked branch of the
+  // captured graph) next to the block's GEMM chain, so its CTAs fill the SMs the GEMMs' partial last waves leave idle.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_conv = getenv("LDMB_NO_FORK") == nullptr;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -293,6 +298,9 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf); release(u.te_pre);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
+  if (u.side_stream) cudaStreamDestroy(u.side_stream);
+  if (u.ev_fork) cudaEventDestroy(u.ev_fork);
+  if (u.ev_join) cudaEventDestroy(u.ev_join);
   if (u.staging) {
     cudaFreeHost(u.staging);
     for (int i = 0; i < kStagingSlots; ++i) if (u.staging_ev[i]) cudaEventDestroy(u.staging_ev[i]);
@@ -643,8 +651,21 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, pl, st));
-  // grouped 3x3 (unet.py:30): x += conv(xm); the residual stream is only ever added to (x itself is not read)
-  if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
+  // grouped 3x3 (unet.py:30): x += conv(xm); the residual stream is only ever added to (x itself is not read),
+  // so the conv is forked onto the side stream and joined at the end of the block
+  // (only where every concurrent update of x is an L2 reduction: halo conv reds, TMA reduce-add GEMM epilogues)
+  const bool fork = u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C);
+  if (fork) {
+    if (!u.side_stream) {
+      CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&u.ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(u.ev_fork, st));
+    CK(cudaStreamWaitEvent(u.side_stream, u.ev_fork, 0));
+    if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false))) return rc;
+    CK(cudaEventRecord(u.ev_join, u.side_stream));
+  } else if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
@@ -667,6 +688,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
       c.out = x; c.ldo = C; c.M = M; c.N = C; c.K = C; c.epi = EPI_ACCUM_F32; c.plan = pl;
       if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
     }
+    if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
     return LDMB_OK;
   }
   {
@@ -682,6 +704,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     c.sel = 2; c.sel_span = C; c.sel_stride = C; c.plan = pl;
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
+  if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
   return LDMB_OK;
 }
 
