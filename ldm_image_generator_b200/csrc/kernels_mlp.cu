@@ -362,7 +362,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       rd2.next(1);
       if (threadIdx.x == 64 && ti == 0) trace_stamp(trace, 7);
     }
-    if (lane == 0) ptx::bulk_wait<0>();
+    if (lane == 0) ptx::bulk_wait_read<0>();                  // smem read by the reduces; the writes complete with the grid
     __syncwarp();
     if (threadIdx.x == 64) trace_stamp(trace, 8);
   }

@@ -258,6 +258,72 @@ __global__ void __launch_bounds__(256) norm_film_kernel(const float* __restrict_
   }
 }
 
+// C = 128 variant: 16 lanes per row (8 channels = two float4 per lane), so one warp normalises TWO pixels x ROWS images
+// per pass and every instruction (index math, shuffles, FiLM arithmetic) serves two rows -- the 32-lanes-per-row
+// kernel above is issue-bound at this width (143 warp instructions per 128-element row, ncu).
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(256) norm_film_c128_kernel(const float* __restrict__ x, const float* __restrict__ film,
+                                                             const int* __restrict__ t_index, T* __restrict__ out,
+                                                             int M, int HW, float eps, const int* __restrict__ skip) {
+  pdl_wait();
+  if (skip != nullptr && *skip != 0) return;
+  constexpr int C = 128;
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const int B = M / HW, groups = (B + ROWS - 1) / ROWS, pairs = (HW + 1) / 2;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < groups * pairs; item += warps_per_grid) {
+    const int p = (item % pairs) * 2 + half, b0 = (item / pairs) * ROWS;
+    const bool pix_ok = p < HW;
+    float4 v[ROWS][2];
+    float sum[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      sum[r] = 0.f;
+      if (pix_ok && b0 + r < B) {
+        const float* xr = x + ((long long)(b0 + r) * HW + p) * C + hl * 8;
+        v[r][0] = __ldg(reinterpret_cast<const float4*>(xr));
+        v[r][1] = __ldg(reinterpret_cast<const float4*>(xr + 4));
+        sum[r] = ((v[r][0].x + v[r][0].y) + (v[r][0].z + v[r][0].w)) + ((v[r][1].x + v[r][1].y) + (v[r][1].z + v[r][1].w));
+      } else {
+        v[r][0] = v[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 mu[2], bi[2];
+    int t_cur = -1;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (b0 + r >= B) break;                          // warp-uniform
+      const int ti = t_index ? t_index[b0 + r] : 0;
+      if (ti != t_cur && pix_ok) {
+        const float* fr = film + ((long long)ti * HW + p) * 2 * C + hl * 8;
+        mu[0] = __ldg(reinterpret_cast<const float4*>(fr)); mu[1] = __ldg(reinterpret_cast<const float4*>(fr + 4));
+        bi[0] = __ldg(reinterpret_cast<const float4*>(fr + C)); bi[1] = __ldg(reinterpret_cast<const float4*>(fr + C + 4));
+      }
+      t_cur = ti;
+      float s1 = sum[r];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);     // within the 16-lane half
+      const float mean = s1 * (1.f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        v[r][i].x -= mean; v[r][i].y -= mean; v[r][i].z -= mean; v[r][i].w -= mean;
+        sq += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rs = 1.f / sqrtf(sq * (1.f / (C - 1)) + eps);      // unbiased variance (modules.py:24)
+      if (pix_ok) {
+        T* orow = out + ((long long)(b0 + r) * HW + p) * C + hl * 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          Pack4<T>::store(orow + 4 * i, fmaf(v[r][i].x * rs, mu[i].x, bi[i].x), fmaf(v[r][i].y * rs, mu[i].y, bi[i].y),
+                          fmaf(v[r][i].z * rs, mu[i].z, bi[i].z), fmaf(v[r][i].w * rs, mu[i].w, bi[i].w));
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void emb_build_kernel(const float* __restrict__ pe, const float* __restrict__ te, T* __restrict__ emb,
                                  int n_t, int HW, int C) {
@@ -848,7 +914,10 @@ template <typename T>
 static cudaError_t norm_film_dispatch(const float* x, const float* film, const int* t_index, T* out, int M, int C,
                                       int HW, float eps, const int* skip, cudaStream_t st) {
   if (M % HW != 0) return cudaErrorInvalidValue;
-  if (C <= 128) norm_film_launch<T, 1, 4>(x, film, t_index, out, M, C, HW, eps, skip, st);
+  if (C == 128) {
+    const long long items = (long long)((M / HW + 3) / 4) * ((HW + 1) / 2);
+    launch_k((norm_film_c128_kernel<T, 4>), grid_for(items * 32, 256, 148 * 8), 256, 0, st, x, film, t_index, out, M, HW, eps, skip);
+  } else if (C <= 128) norm_film_launch<T, 1, 4>(x, film, t_index, out, M, C, HW, eps, skip, st);
   else if (C <= 256) norm_film_launch<T, 2, 4>(x, film, t_index, out, M, C, HW, eps, skip, st);
   else if (C <= 512) norm_film_launch<T, 4, 2>(x, film, t_index, out, M, C, HW, eps, skip, st);
   else if (C <= 1024) norm_film_launch<T, 8, 1>(x, film, t_index, out, M, C, HW, eps, skip, st);

@@ -489,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (tl.tma_out && lane == 0) ptx::bulk_wait<0>();       // all of this warp's stores have landed
+    if (tl.tma_out && lane == 0) ptx::bulk_wait_read<0>();  // the stores have read their smem slabs; the writes themselves complete with the grid
     __syncwarp();
     if (threadIdx.x == 64) trace_stamp(trace, 8);            // epilogue done
   }
