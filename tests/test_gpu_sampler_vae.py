@@ -120,3 +120,35 @@ def test_vae_roundtrip_shapes_and_wrapper():
     assert tuple(y.shape) == (2, 3, 32, 48)
     want = R.decoder_forward(R.make_decoder_state(dc, 5), dc, R.encoder_forward(R.make_encoder_state(ec, 5), ec, x.cpu()))
     assert R.rel_l2(y.cpu(), want) < 1e-5
+
+
+def test_film_precompute_chunks_and_per_step_path_agree():
+    """DDPM.sample evaluates the Encodings MLP (unet.py:18-21) for all timesteps of the schedule up front, in chunks
+    bounded by a memory budget.  One chunk, many small chunks and the per-step evaluation (UNet.forward outside
+    sample) must give the same trajectory: bit-identical in fp32 validation mode."""
+    import random
+    from ldm_image_generator_b200 import _lib
+    d, shape = _ddpm("fp32")
+    d.eval()
+    fix = golden("ddim_tiny")
+    steps = [0, 30, 60, 90, 120, 150, 199]
+    one = d.sample(shape, seed=5, num_steps=7, schedule=steps, x_T=fix["x_T"], progress=False)
+    old = d.model.FILM_BYTES_BUDGET
+    try:
+        d.model.FILM_BYTES_BUDGET = 1                      # film_chunk() == 1: a precompute call per step
+        assert d.model.film_chunk(shape[2], shape[3]) == 1
+        many = d.sample(shape, seed=5, num_steps=7, schedule=steps, x_T=fix["x_T"], progress=False)
+    finally:
+        d.model.FILM_BYTES_BUDGET = old
+    assert torch.equal(one, many)
+    # the same updates driven step by step through the public forward (no precomputed tables)
+    random.seed(5)
+    x = fix["x_T"].cuda().float().clone()
+    alpha = torch.cumprod(1 - d.beta, dim=0)
+    for t, t_next in d.timesteps(7, steps):
+        co, _ = d.ddim_scalars(alpha, int(t), int(t_next), 0)
+        eps = d.model(x=x, time=torch.full((shape[0],), int(t), device="cuda"), condition=None)
+        x0 = (x - co.c_eps_in * eps) / co.c_div
+        x = x0 if int(t) == 0 else co.c_x0 * x0 + co.c_eps_out * eps
+    assert R.rel_l2(x.cpu(), one.cpu()) < 1e-6
+    assert_no_fault(d.model)
