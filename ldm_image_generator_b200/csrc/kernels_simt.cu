@@ -354,6 +354,35 @@ __global__ void pool2_kernel(const TI* __restrict__ x, TO* __restrict__ out, int
   }
 }
 
+// AvgPool2d(2) fp32 NHWC -> T, four channels per thread (16-byte loads)
+template <typename TO>
+__global__ void pool2_vec4_kernel(const float* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C4) {
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const float4* p = x4 + (((long long)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const float4 a = __ldg(p), bq = __ldg(p + C4), cq = __ldg(p + (long long)W * C4), d = __ldg(p + (long long)W * C4 + C4);
+    Pack4<TO>::store(out + i * 4, ((a.x + bq.x) + (cq.x + d.x)) * 0.25f, ((a.y + bq.y) + (cq.y + d.y)) * 0.25f,
+                     ((a.z + bq.z) + (cq.z + d.z)) * 0.25f, ((a.w + bq.w) + (cq.w + d.w)) * 0.25f);
+  }
+}
+
+template <typename T>
+__global__ void cast_vec4_kernel(const float* __restrict__ x, T* __restrict__ out, long long n4) {
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    Pack4<T>::store(out + i * 4, v.x, v.y, v.z, v.w);
+  }
+}
+
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
   pdl_wait();
@@ -943,6 +972,11 @@ cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool i
 
 cudaError_t launch_pool_cast(const float* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * C;
+  if (C % 4 == 0) {
+    if (is_bf16) launch_k((pool2_vec4_kernel<bf16>), grid_for(total / 4, 256), 256, 0, st, x, (bf16*)out, B, H, W, C / 4);
+    else launch_k((pool2_vec4_kernel<float>), grid_for(total / 4, 256), 256, 0, st, x, (float*)out, B, H, W, C / 4);
+    return cudaGetLastError();
+  }
   if (is_bf16) launch_k((pool2_kernel<float, bf16>), grid_for(total, 256), 256, 0, st, x, (bf16*)out, B, H, W, C);
   else launch_k((pool2_kernel<float, float>), grid_for(total, 256), 256, 0, st, x, (float*)out, B, H, W, C);
   return cudaGetLastError();
@@ -956,6 +990,11 @@ cudaError_t launch_pool_t(const void* x, void* out, bool is_bf16, int B, int H, 
 }
 
 cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cudaStream_t st) {
+  if (n % 4 == 0) {
+    if (is_bf16) launch_k((cast_vec4_kernel<bf16>), grid_for(n / 4, 256), 256, 0, st, x, (bf16*)out, n / 4);
+    else launch_k((cast_vec4_kernel<float>), grid_for(n / 4, 256), 256, 0, st, x, (float*)out, n / 4);
+    return cudaGetLastError();
+  }
   if (is_bf16) launch_k((cast_kernel<bf16>), grid_for(n, 256), 256, 0, st, x, (bf16*)out, n);
   else launch_k((cast_kernel<float>), grid_for(n, 256), 256, 0, st, x, (float*)out, n);
   return cudaGetLastError();
