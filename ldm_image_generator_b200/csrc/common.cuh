@@ -15,7 +15,10 @@ enum { EPI_STORE = 0,      // out(T)[m,n]   = act(acc + bias) (+ res)
        EPI_STORE_F32 = 1,  // out(f32)[m,n] = act(acc + bias)
        EPI_ACCUM_F32 = 2,  // out(f32)[m,n] += acc + bias           (residual stream)
        EPI_REGLU = 3,      // out(T)[m,j]   = (acc_a + bias_a) * relu(acc_b + bias_b)   (modules.py:15)
-       EPI_CONVT = 4 };    // ConvTranspose2d(k=2,s=2): column n = (dy*2+dx)*Cout + co scattered to pixel (2h+dy, 2w+dx)
+       EPI_CONVT = 4,      // ConvTranspose2d(k=2,s=2): column n = (dy*2+dx)*Cout + co scattered to pixel (2h+dy, 2w+dx)
+       EPI_UPADD = 5 };    // out(f32)[2x2 pixels of the nearest-upsampled row m, n] += acc + bias  (unet.py:85,100-101: the 1x1
+                           // conv commutes with nearest Upsample(2), so the conv runs at low resolution and its result is
+                           // replicated into the skip-connected residual stream); ctH, ctW = low-resolution height, width
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
 // One GEMM-shaped launch: acc[M, N] = A[M, K] * W[N, K]^T, then an epilogue.  Used by both the

@@ -57,8 +57,6 @@ cudaError_t launch_emb_build(const float* pe, const float* te, void* emb, bool i
 // AvgPool2d(2) on NHWC fp32 -> T (feeds the encoder ch_conv GEMM; pool and 1x1 conv commute, unet.py:83)
 cudaError_t launch_pool_cast(const float* x, void* out, bool is_bf16, int B, int H, int W, int C, cudaStream_t st);
 cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cudaStream_t st);
-// x[b,h,w,:] += ylow[b,h/2,w/2,:]   (nearest Upsample(2) commuted behind the 1x1 conv + skip add, unet.py:85,100-101)
-cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st);
 // Window attention core (attention.py:13-85 + torch MHA): qkv(T) [M,3C] (+ in_proj bias for pad tokens),
 // key bias from xm(T) channel 0 when shift != 0, writes att(T) rows of stride ldo
 cudaError_t launch_window_attention(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,

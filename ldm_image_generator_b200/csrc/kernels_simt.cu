@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc dparam) {
           *o += v;
         } else if (d.epi == EPI_STORE_F32) {
           reinterpret_cast<float*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = apply_act(v, d.act, d.slope);
+        } else if (d.epi == EPI_UPADD) {
+          const int HW = d.ctH * d.ctW, b = m / HW, r = m % HW, hh = r / d.ctW, ww = r % d.ctW;
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float*>(d.out)[(((long long)b * 2 * d.ctH + 2 * hh + (q >> 1)) * 2 * d.ctW + 2 * ww + (q & 1)) * d.ldo + j] += v;
         } else if (d.epi == EPI_CONVT) {
           reinterpret_cast<T*>(d.out)[convt_offset(d, m, j)] = from_f<T>(apply_act(v, d.act, d.slope));
         } else {
@@ -388,25 +392,6 @@ __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, lo
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = from_f<T>(x[i]);
-}
-
-__global__ void upsample_add_kernel(float* __restrict__ x, const float* __restrict__ ylow, int B, int H, int W, int C4) {
-  pdl_wait();
-  // C4 = C / 4 (float4 lanes)
-  const long long total = (long long)B * H * W * C4;
-  float4* x4 = reinterpret_cast<float4*>(x);
-  const float4* y4 = reinterpret_cast<const float4*>(ylow);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    long long t = i / C4;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int b = (int)(t / H);
-    const float4 y = __ldg(y4 + (((long long)b * (H / 2) + h / 2) * (W / 2) + w / 2) * C4 + c);
-    float4 v = x4[i];
-    v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
-    x4[i] = v;
-  }
 }
 
 // =====================================================================================
@@ -997,13 +982,6 @@ cudaError_t launch_cast(const float* x, void* out, bool is_bf16, long long n, cu
   }
   if (is_bf16) launch_k((cast_kernel<bf16>), grid_for(n, 256), 256, 0, st, x, (bf16*)out, n);
   else launch_k((cast_kernel<float>), grid_for(n, 256), 256, 0, st, x, (float*)out, n);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_upsample_add(float* x, const float* ylow, int B, int H, int W, int C, cudaStream_t st) {
-  if (C % 4 != 0) return cudaErrorNotSupported;
-  const long long total = (long long)B * H * W * (C / 4);
-  launch_k((upsample_add_kernel), grid_for(total, 256), 256, 0, st, x, ylow, B, H, W, C / 4);
   return cudaGetLastError();
 }
 

@@ -437,6 +437,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             for (int i = 0; i < 32; ++i) if (n + i < d.N) o[i] += v[i];
           }
+        } else if (d.epi == EPI_UPADD) {
+          // the low-resolution row feeds the 2x2 pixels of its nearest-upsampled position; x is only added to here
+          const int HW = d.ctH * d.ctW, bb = m / HW, rr = m % HW, hh = rr / d.ctW, ww = rr % d.ctW;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float* o = reinterpret_cast<float*>(d.out) +
+                       (((long long)bb * 2 * d.ctH + 2 * hh + (q4 >> 1)) * 2 * d.ctW + 2 * ww + (q4 & 1)) * d.ldo + n;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                             "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+            } else {
+              for (int i = 0; i < 32; ++i) if (n + i < d.N) atomicAdd(o + i, v[i]);
+            }
+          }
         } else if (d.epi == EPI_STORE_F32) {
           float* o = reinterpret_cast<float*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + n;
 #pragma unroll
@@ -710,7 +726,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   tl.tma_out = 0; tl.out_col_b = 0; tl.out_row_b = 0;
   {
     const bool f32 = d.epi == EPI_STORE_F32 || d.epi == EPI_ACCUM_F32;
-    const bool mode_ok = (d.epi == EPI_STORE || d.epi == EPI_REGLU || f32) && d.res == nullptr;
+    const bool mode_ok = (d.epi == EPI_STORE || d.epi == EPI_REGLU || f32) && d.res == nullptr;   // (EPI_UPADD scatters: direct path)
     const int esz = f32 ? 4 : 2;
     const int slab_cols = f32 ? 32 : 64;
     const int out_n = d.epi == EPI_REGLU ? d.N / 2 : d.N;

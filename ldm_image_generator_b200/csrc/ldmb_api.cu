@@ -82,7 +82,7 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, pooled, ylow, stepbuf, te_pre;
+  DevBuf xm, hbuf, qkv, pooled, stepbuf, te_pre;
   // FiLM tables precomputed for a whole schedule (ldmb_unet_precompute_film): film holds n_t = film_nt timesteps
   int film_nt = 0, film_Hs = 0, film_Ws = 0;
   // device views into stepbuf (layout fixed per (B, n_t)): StepParams | plan[n_blocks][4] | t_index[B] | te tables
@@ -295,7 +295,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.ylow); release(u.stepbuf); release(u.te_pre);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.stepbuf); release(u.te_pre);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
   if (u.side_stream) cudaStreamDestroy(u.side_stream);
@@ -599,7 +599,6 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
   if ((rc = ensure(h, u.hbuf, mx_mc * 4 * ts))) return rc;
   if ((rc = ensure(h, u.qkv, mx_mc * 3 * ts))) return rc;
   if ((rc = ensure(h, u.pooled, (mx_low ? mx_low : 64) * ts))) return rc;
-  if ((rc = ensure(h, u.ylow, (mx_low ? mx_low : 64) * 4))) return rc;
   return LDMB_OK;
 }
 
@@ -760,16 +759,16 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
   for (int l = S - 1; l >= 0; --l) {
     const int Hl = Hs >> l, Wl = Ws >> l;
     if (l < S - 1) {
-      // ch_conv = Upsample(2, nearest) then Conv1x1 (unet.py:85): conv at low resolution, replicate on the skip add
+      // ch_conv = Upsample(2, nearest) then Conv1x1 (unet.py:85): conv at low resolution, replicated into the skip-connected
+      // residual stream by the GEMM's epilogue (EPI_UPADD)
       LevelW& L = u.levels[l];
       const int C = L.C, Cn = cfg.channels[l + 1];
       const long long Mlow = (long long)B * (Hl / 2) * (Wl / 2);
       CKL(launch_cast(static_cast<const float*>(u.levels[l + 1].xs.p), u.pooled.p, h->bf16(), Mlow * Cn, st));
       GemmDesc d = gd();
-      d.A = u.pooled.p; d.lda = Cn; d.W = L.w_up; d.ldw = Cn; d.bias = L.b_up; d.out = u.ylow.p; d.ldo = C;
-      d.M = (int)Mlow; d.N = C; d.K = Cn; d.epi = EPI_STORE_F32;
+      d.A = u.pooled.p; d.lda = Cn; d.W = L.w_up; d.ldw = Cn; d.bias = L.b_up; d.out = L.xs.p; d.ldo = C;
+      d.M = (int)Mlow; d.N = C; d.K = Cn; d.epi = EPI_UPADD; d.ctH = Hl / 2; d.ctW = Wl / 2;   // x_l += up2(conv(x_{l+1})) in the epilogue
       if ((rc = gemm(h, d, st, PK_LEVEL))) return rc;
-      CKL(launch_upsample_add(static_cast<float*>(L.xs.p), static_cast<const float*>(u.ylow.p), B, Hl, Wl, C, st));
     }
     for (int b = 0; b < cfg.blocks[l]; ++b, ++bi)
       if ((rc = run_block(h, u.blocks[bi], bi, B, Hl, Wl, n_t, st))) return rc;
