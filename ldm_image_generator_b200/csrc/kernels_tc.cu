@@ -37,6 +37,7 @@ struct TcTiling {
   int m_tiles, n_tiles, num_kb, total;
   int TW, TH, TB;   // AM_CONV3: the 128-pixel tile is TB images x TH rows x TW columns
   int tma_out;      // epilogue goes through smem + TMA store / reduce
+  int max_stages;       // debug (LDMB_TC_STAGES): use only this many of the smem pipeline stages
   int splits, kb_per;   // split-K (EPI_ACCUM_F32 through TMA reduce-add only): tile t covers k-blocks [sp*kb_per, ...)
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
 };
@@ -91,15 +92,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault, long long* trace) {
   using Cfg = TcCfg<BN, CG>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES_MAX = Cfg::STAGES;
+  const int STAGES = tl.max_stages > 0 && tl.max_stages < STAGES_MAX ? tl.max_stages : STAGES_MAX;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;   // position in the CTA pair
   const bool leader = rank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = tiles + STAGES * Cfg::STAGE_BYTES;      // 1024-aligned (every stage is a multiple of 1024 B)
+  uint8_t* staging = tiles + STAGES_MAX * Cfg::STAGE_BYTES;      // 1024-aligned (every stage is a multiple of 1024 B)
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + STAGES_MAX;
+  uint64_t* tfull = empty + STAGES_MAX;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -645,6 +647,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
     attr_set = true;
   }
   int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
+  if (getenv("LDMB_TC_GRID") && atoi(getenv("LDMB_TC_GRID")) < grid) grid = (atoi(getenv("LDMB_TC_GRID")) / CG) * CG;   // debug
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
@@ -680,6 +683,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   tl.num_kb = d.K / BK;
   tl.total = tl.m_tiles * tl.n_tiles * batch;
   tl.splits = 1; tl.kb_per = tl.num_kb;
+  tl.max_stages = getenv("LDMB_TC_STAGES") ? atoi(getenv("LDMB_TC_STAGES")) : 0;
   tl.TW = tl.TH = tl.TB = 0;
 
   CUtensorMap tmA, tmB;
