@@ -102,6 +102,12 @@ int ldmb_set_force_simt(ldmb_handle* h, int on);
  * device-side step buffer.  Off = every kernel launched individually. */
 int ldmb_set_use_graphs(ldmb_handle* h, int on);
 /* Number of kernels this library has launched on the handle since creation (graph replays count their kernels). */
+/* bf16 mode adds the branch outputs of a block into the fp32 residual stream with L2 reductions; with split-K GEMM
+ * slices and the grouped conv running as a concurrent graph branch their arrival order varies, so two runs agree only
+ * to fp32 rounding of x (then re-quantised by later bf16 roundings: ~1e-3 rel-L2 at the default UNet, inside the 1e-2
+ * parity budget).  on != 0: no split-K, no concurrent branch -> bit-reproducible results (a few % slower).
+ * Also enabled by the environment variable LDMB_DETERMINISTIC. */
+int ldmb_set_deterministic(ldmb_handle* h, int on);
 int64_t ldmb_launch_count(const ldmb_handle* h);
 /* 0, or the watchdog code a tcgen05 pipeline wrote when an mbarrier wait timed out (device read; synchronises). */
 int ldmb_check_device_fault(ldmb_handle* h, void* stream);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ldmb_check_device_fault": (C.c_int, [_H, _P]),
     "ldmb_debug_tc_trace": (C.c_int, [_H, C.c_int, _I64P, C.c_int]),
     "ldmb_unet_precompute_film": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.POINTER(_P), _P]),
+    "ldmb_set_deterministic": (C.c_int, [_H, C.c_int]),
     "ldmb_debug_skip_classes": (C.c_int, [_H, C.c_uint32]),
     "ldmb_profile_begin": (C.c_int, [_H]),
     "ldmb_profile_end": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64P]),

@@ -14,6 +14,7 @@ void tc_context_destroy(TcContext*);
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s);
 bool tc_supported(const GemmDesc& d);
 int tc_read_fault(TcContext* ctx, cudaStream_t s);
+void tc_set_splitk(TcContext* ctx, bool on);
 // debug: per-CTA %globaltimer stamps (16 slots per CTA) of the most recent tcgen05 launch
 int tc_trace_enable(TcContext* ctx, int on);
 int tc_trace_read(TcContext* ctx, long long* host, int max_ctas);

@@ -580,6 +580,7 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   ctx->encode = nullptr;
   ctx->fault_dev = nullptr;
   ctx->trace_dev = nullptr;
+  ctx->splitk = true;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -628,6 +629,8 @@ int tc_trace_read(TcContext* ctx, long long* host, int max_ctas) {
   if (cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * kTraceSlots * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
 }
+
+void tc_set_splitk(TcContext* ctx, bool on) { ctx->splitk = on; }
 
 int tc_read_fault(TcContext* ctx, cudaStream_t s) {
   int v = 0;
@@ -754,7 +757,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   }
   // split-K: an accumulate-into-the-residual GEMM with too few output tiles to fill the machine (deep UNet levels:
   // M = 1024..4096 rows, K = 3C..4C) is cut along K; every slice reduce-adds its partial tile into x with TMA.
-  if (tl.tma_out && d.epi == EPI_ACCUM_F32 && g_tc_splitk) {
+  if (tl.tma_out && d.epi == EPI_ACCUM_F32 && g_tc_splitk && ctx->splitk) {
     const int base = tl.total * cg;
     int sp = ctx->num_sms / (base > 0 ? base : 1);
     if (sp > tl.num_kb / 4) sp = tl.num_kb / 4;              // at least 4 k-blocks (K = 256) per slice

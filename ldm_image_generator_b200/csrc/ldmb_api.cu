@@ -284,6 +284,7 @@ extern "C" int ldmb_create(int device, int precision, ldmb_handle** out) {
     delete h;
     return LDMB_ERR_CUDA;
   }
+  if (getenv("LDMB_DETERMINISTIC")) ldmb_set_deterministic(h, 1);
   *out = h;
   return LDMB_OK;
 }
@@ -780,6 +781,14 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
 }
 
 }  // namespace
+
+extern "C" int ldmb_set_deterministic(ldmb_handle* h, int on) {
+  if (!h) return LDMB_ERR_INVALID;
+  tc_set_splitk(h->tc, on == 0);
+  h->unet.fork_conv = on == 0 && getenv("LDMB_NO_FORK") == nullptr;
+  h->unet.ws_epoch++;          // captured graphs hold the old launch set
+  return LDMB_OK;
+}
 
 extern "C" int ldmb_set_use_graphs(ldmb_handle* h, int on) {
   if (!h) return LDMB_ERR_INVALID;

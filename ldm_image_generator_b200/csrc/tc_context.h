@@ -12,4 +12,5 @@ struct TcContext {
   int* fault_dev;
   int device;
   long long* trace_dev;   // debug: per-CTA %globaltimer stamps of the last launch (NULL unless enabled)
+  bool splitk;            // split-K for the residual GEMMs (off in deterministic mode: slices reduce-add in arrival order)
 };

@@ -88,6 +88,10 @@ class Handle:
     def set_force_simt(self, on: bool) -> None:
         self.check(self.lib.ldmb_set_force_simt(self.h, int(on)))
 
+    def set_deterministic(self, on: bool) -> None:
+        """Bit-reproducible bf16 results (no split-K slices, no concurrent conv branch); see ldmb.h."""
+        self.check(self.lib.ldmb_set_deterministic(self.h, int(on)))
+
     def set_use_graphs(self, on: bool) -> None:
         self.check(self.lib.ldmb_set_use_graphs(self.h, int(on)))
 

@@ -92,6 +92,7 @@ class UNet(nn.Module):
         self._handle: Optional[runtime.Handle] = None
         self._pe_res = None
         self._film = None      # (handle, (H, W), {t: row}) of the FiLM tables precomputed for a schedule
+        self._deterministic = False
 
     # ------------------------------------------------------------------ host-side helpers
     def set_precision(self, precision: str) -> "UNet":
@@ -100,6 +101,14 @@ class UNet(nn.Module):
             raise ValueError(precision)
         if precision != self.precision:
             self.precision, self._handle, self._pe_res, self._film = precision, None, None, None
+        return self
+
+    def set_deterministic(self, on: bool = True) -> "UNet":
+        """bf16 mode: bit-reproducible (and batch-size independent) results at a few % of speed -- no split-K GEMM
+        slices, no concurrent grouped-conv branch, so every element of the residual stream is updated in a fixed order."""
+        self._deterministic = bool(on)
+        if self._handle is not None:
+            self._handle.set_deterministic(self._deterministic)
         return self
 
     def blocks_in_execution_order(self) -> List[SwinBlock]:
@@ -129,6 +138,7 @@ class UNet(nn.Module):
         if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
             h = runtime.Handle(device, self.precision)
             h.unet_configure(self.input_channels, self.stage_blocks, self.stage_channels, self.stem_size)
+            h.set_deterministic(self._deterministic)
             self._handle, self._pe_res, self._film = h, None, None
             check_params = True
         if check_params:
