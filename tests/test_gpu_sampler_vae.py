@@ -152,3 +152,27 @@ def test_film_precompute_chunks_and_per_step_path_agree():
         x = x0 if int(t) == 0 else co.c_x0 * x0 + co.c_eps_out * eps
     assert R.rel_l2(x.cpu(), one.cpu()) < 1e-6
     assert_no_fault(d.model)
+
+
+def test_full_size_decode_vs_oracle_and_shard_equivalence():
+    """BASELINE configs[1] decode size: the default Decoder on a multi-image batch of 8x32x32 latents -> 256x256 RGB
+    (multi-tile paths of every conv level, the halo-patch kernel at 64 channels, the fused uint8 output).  Two of the images
+    against the CPU oracle; the decoder has no reductions into shared state, so a batch is bit-identical to its shards."""
+    cfg = R.DecoderCfg()
+    sd = R.make_decoder_state(cfg, 1234)
+    dec = build_decoder(cfg, sd, "bf16")
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(12, 8, 32, 32, generator=g)
+    with torch.no_grad():
+        y = dec(z.cuda()).cpu()
+        u8 = dec.decode_to_uint8(z.cuda()).cpu()
+        shards = torch.cat([dec(z[i:i + 4].cuda()).cpu() for i in range(0, 12, 4)])
+    assert torch.equal(shards, y)
+    pick = [0, 11]
+    want = R.decoder_forward(sd, cfg, z[pick])
+    err, db = R.rel_l2(y[pick], want), R.psnr(y[pick].clamp(-1, 1), want.clamp(-1, 1))
+    print(f"full-size decode: rel-L2 {err:.3e} PSNR {db:.1f} dB")
+    assert err < 1e-2 and db >= PSNR_MIN_DB
+    assert tuple(u8.shape) == (12, 256, 256, 3)
+    assert int((u8[pick].int() - R.to_uint8_image(want).int()).abs().max()) <= 3
+    assert_no_fault(dec)
