@@ -92,7 +92,7 @@ class UNet(nn.Module):
         self._handle: Optional[runtime.Handle] = None
         self._pe_res = None
         self._film = None      # (handle, (H, W), {t: row}) of the FiLM tables precomputed for a schedule
-        self._deterministic = False
+        self._deterministic = None     # None: the library default (environment variable LDMB_DETERMINISTIC)
 
     # ------------------------------------------------------------------ host-side helpers
     def set_precision(self, precision: str) -> "UNet":
@@ -138,7 +138,8 @@ class UNet(nn.Module):
         if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
             h = runtime.Handle(device, self.precision)
             h.unet_configure(self.input_channels, self.stage_blocks, self.stage_channels, self.stem_size)
-            h.set_deterministic(self._deterministic)
+            if self._deterministic is not None:
+                h.set_deterministic(self._deterministic)
             self._handle, self._pe_res, self._film = h, None, None
             check_params = True
         if check_params:
