@@ -167,6 +167,15 @@ int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B,
                       const int32_t* plan, const ldmb_ddim_coef* coef, const float* noise_dev,
                       void* stream);
 
+/* The same step with PER-IMAGE stochastic-depth / expert decisions: plan_img is host int32 [n_blocks][B][3] =
+ * (skip, e1, e2) of block k for image b.  This is what a batch of the reference's batch-1 calls computes (its sample
+ * scripts loop `sample((1, ...))`, sample_ldm.py:71-72 / sample_ddpm.py:35-36, so every image draws its own decisions
+ * from Python's `random`).  Exact: all five ReGLU experts are evaluated and the image's choice is applied by masking. */
+int ldmb_unet_forward_per_image(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
+                                const int32_t* t_index, int n_t, const float* const* te_host,
+                                const int32_t* plan_img, const ldmb_ddim_coef* coef, const float* noise_dev,
+                                void* stream);
+
 /* The Encodings MLP (unet.py:18-21) of every block for ALL n_t timesteps of a sampling schedule in one batched pass
  * (its weights, 58 % of the parameters, are then streamed once per schedule instead of once per step).
  * te_host as in ldmb_unet_forward.  Valid until the next ldmb_unet_load_param / ldmb_unet_forward with te_host != NULL. */

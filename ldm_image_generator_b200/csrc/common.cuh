@@ -33,7 +33,8 @@ struct GemmDesc {
   int M, N, K;                         // N counts accumulator columns
   int epi, act; float slope;
   // expert selection (RandomMoE, modules.py:34-36): which rows of the stacked expert weights a slot uses
-  int sel;                             // 0 none; 1 slot = n / sel_span (a|b GEMM); 2 slot = k / sel_span (c GEMM)
+  int sel;                             // 0 none; 1 slot = n / sel_span (a|b GEMM); 2 slot = k / sel_span (c GEMM);
+                                       // 3 like 2 with every slot in order: slot q uses rows q * sel_stride (per-image plans)
   int sel_span;
   int sel_rows[4];                     // first weight row (and bias index) of slot 0..3
   // Device-side plan entry {skip, e1, e2, -} of the SwinBlock this launch belongs to (NULL: use sel_rows as given).
@@ -57,7 +58,7 @@ struct StepParams {
 __device__ __forceinline__ bool resolve_plan(GemmDesc& d) {
   if (d.plan == nullptr) return false;
   if (d.plan[0] != 0) return true;
-  if (d.sel != 0) {
+  if (d.sel == 1 || d.sel == 2) {
     d.sel_rows[0] = 0;
     d.sel_rows[1] = (1 + d.plan[1]) * d.sel_stride;
     d.sel_rows[2] = (1 + d.plan[2]) * d.sel_stride;
@@ -112,9 +113,9 @@ __device__ __forceinline__ int wrow_of_col(const GemmDesc& d, int z, int n) {
 __device__ __forceinline__ float bias_of_col(const GemmDesc& d, int z, int n) {
   if (d.bias == nullptr) return 0.f;
   const float* b = d.bias + z * d.bias_off_b;
-  if (d.sel == 2) {
+  if (d.sel == 2 || d.sel == 3) {
     float s = 0.f;
-    for (int q = 0; q < d.K / d.sel_span; ++q) s += b[d.sel_rows[q] + n];
+    for (int q = 0; q < d.K / d.sel_span; ++q) s += b[(d.sel == 3 ? q * d.sel_stride : d.sel_rows[q]) + n];
     return s;
   }
   if (d.sel == 1) return b[d.sel_rows[n / d.sel_span] + n % d.sel_span];

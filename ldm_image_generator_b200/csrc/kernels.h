@@ -74,6 +74,11 @@ cudaError_t launch_window_attention_mma(const void* qkv, const void* xm, const f
 cudaError_t launch_final(const float* x, const float* w, const float* bias, const StepParams* sp,
                          int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
 
+// ---- per-image plans (plan word per image: skip | e1 << 8 | e2 << 16; see kernels_simt.cu)
+cudaError_t launch_mask_experts(void* h, long long ldh, bool is_bf16, const int* plan_img, int M, int HW, int C, cudaStream_t st);
+cudaError_t launch_rows_bias(float* x, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn, cudaStream_t st);
+cudaError_t launch_skip_rows(float* x, float* backup, const int* plan_img, int M, int HW, int C, bool restore, cudaStream_t st);
+
 // ---- VAE pieces
 // 1x1 conv from an NCHW fp32 tensor with few channels (latent 8 / RGB 3) into NHWC T
 cudaError_t launch_nchw_pointwise_in(const float* x, const float* w, const float* bias, void* out, bool is_bf16,

@@ -139,9 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   bool skip_block = false;
   if (d.plan != nullptr) {
     skip_block = d.plan[0] != 0;   // stochastic depth skipped this block for this step (uniform over the grid)
-    if (d.sel != 0) { srow0 = 0; srow1 = (1 + d.plan[1]) * d.sel_stride; srow2 = (1 + d.plan[2]) * d.sel_stride; srow3 = 5 * d.sel_stride; }
+    if (d.sel == 1 || d.sel == 2) { srow0 = 0; srow1 = (1 + d.plan[1]) * d.sel_stride; srow2 = (1 + d.plan[2]) * d.sel_stride; srow3 = 5 * d.sel_stride; }
   }
-  auto srow = [&](int q) { return q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3)); };
+  const bool sel_k = d.sel == 2 || d.sel == 3;        // weight rows selected per K slot
+  auto srow = [&](int q) { return d.sel == 3 ? q * d.sel_stride : (q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3))); };
   const int total_tiles = skip_block ? 0 : tl.total;
   const bool is_producer = warp == 0 && lane == 0;
   if (!is_producer) {
@@ -154,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       auto b_coords = [&](int z, int n0, int kk, int& brow, int& bcol) {
         bcol = kk;
-        if (d.sel == 2) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
+        if (sel_k) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
         else if (d.sel == 1) brow = srow(n0 / d.sel_span) + n0 % d.sel_span;
         else brow = n0;
         brow += (int)(z * d.w_row_b) + (int)rank * Cfg::B_ROWS;      // this CTA's share of the tile's weight rows
@@ -279,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float bv = 0.f;
         if (n < d.N && d.bias != nullptr && sp == 0) {      // split-K: the bias rides with the first K slice
           const float* bp = d.bias + z * d.bias_off_b;
-          if (d.sel == 2) { for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; }
+          if (sel_k) { for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; }
           else if (d.sel == 1) bv = bp[srow(n / d.sel_span) + n % d.sel_span];
           else bv = bp[n];
         }
@@ -565,7 +566,7 @@ bool tc_supported(const GemmDesc& d) {
     if (d.cC % BK || d.lda % 8 || d.a_koff_b % 8) return false;
     if (!conv_tile(d, a, b, c)) return false;
   }
-  if (d.sel == 2 && d.sel_span % BK) return false;
+  if ((d.sel == 2 || d.sel == 3) && d.sel_span % BK) return false;
   if (d.epi == EPI_REGLU && d.glu_chunk != 64) return false;
   if (d.epi == EPI_CONVT && d.ctC % 32) return false;
   if (d.epi != EPI_CONVT && (d.ldo % 8 || d.out_off_b % 8)) return false;
@@ -721,6 +722,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
     if (d.sel == 2) { rows = 0; for (int q = 0; q < d.K / d.sel_span; ++q) if (d.sel_rows[q] + d.N > rows) rows = d.sel_rows[q] + d.N; }
     if (d.plan != nullptr && d.sel == 1) rows = 5LL * d.sel_stride;      // any expert may be picked at replay time
     if (d.plan != nullptr && d.sel == 2) rows = (d.K / d.sel_span == 4 ? 6LL : 5LL) * d.sel_stride;
+    if (d.sel == 3) rows = (long long)(d.K / d.sel_span - 1) * d.sel_stride + d.N;
     rows += (long long)(batch - 1) * d.w_row_b;
     const cuuint64_t gdim[2] = {(cuuint64_t)d.ldw, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)d.ldw * 2};

@@ -82,12 +82,14 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, pooled, stepbuf, te_pre;
+  DevBuf xm, hbuf, qkv, pooled, stepbuf, te_pre, backup;
+  const int* plan_img_dev = nullptr;   // per-image plans [n_blocks][B] (skip | e1 << 8 | e2 << 16), NULL in the shared-plan mode
+  bool per_image_ws = false;           // workspaces sized for the per-image path (hbuf 6C wide, skip backup)
   // FiLM tables precomputed for a whole schedule (ldmb_unet_precompute_film): film holds n_t = film_nt timesteps
   int film_nt = 0, film_Hs = 0, film_Ws = 0;
   // device views into stepbuf (layout fixed per (B, n_t)): StepParams | plan[n_blocks][4] | t_index[B] | te tables
   const StepParams* sp_dev = nullptr; const int* plan_dev = nullptr; const int* tindex_dev = nullptr;
-  struct GraphEntry { int B, Hs, Ws, n_t, pre; unsigned long long epoch; cudaGraphExec_t exec; long long launches; int seen; };
+  struct GraphEntry { int B, Hs, Ws, n_t, pre, per_image; unsigned long long epoch; cudaGraphExec_t exec; long long launches; int seen; };
   std::vector<GraphEntry> graphs;
   unsigned long long ws_epoch = 0;     // bumped whenever a workspace is reallocated (cached graphs hold raw pointers)
   bool use_graphs = true;
@@ -296,7 +298,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.stepbuf); release(u.te_pre);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.stepbuf); release(u.te_pre); release(u.backup);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
   if (u.side_stream) cudaStreamDestroy(u.side_stream);
@@ -576,7 +578,7 @@ extern "C" int ldmb_unet_load_param(ldmb_handle* h, const char* name, const floa
 // =====================================================================================
 namespace {
 
-int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: post-stem resolution
+int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t, bool per_image = false) {   // Hs, Ws: post-stem resolution
   UNetState& u = h->unet;
   const int S = u.cfg.num_levels;
   const size_t ts = h->tsize();
@@ -597,7 +599,9 @@ int unet_reserve(ldmb_handle* h, int B, int Hs, int Ws, int n_t) {   // Hs, Ws: 
     }
   }
   if ((rc = ensure(h, u.xm, mx_mc * ts))) return rc;
-  if ((rc = ensure(h, u.hbuf, mx_mc * 4 * ts))) return rc;
+  if (per_image) u.per_image_ws = true;
+  if ((rc = ensure(h, u.hbuf, mx_mc * (u.per_image_ws ? 6 : 4) * ts))) return rc;   // per-image plans: all five experts + attention
+  if (u.per_image_ws && (rc = ensure(h, u.backup, mx_mc * 4))) return rc;
   if ((rc = ensure(h, u.qkv, mx_mc * 3 * ts))) return rc;
   if ((rc = ensure(h, u.pooled, (mx_low ? mx_low : 64) * ts))) return rc;
   return LDMB_OK;
@@ -640,8 +644,11 @@ extern "C" int ldmb_unet_set_position_table(ldmb_handle* h, int level, const flo
 
 namespace {
 
+int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, int Wl, int n_t, cudaStream_t st);
+
 int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, int Wl, int n_t, cudaStream_t st) {
   UNetState& u = h->unet;
+  if (u.plan_img_dev != nullptr) return run_block_per_image(h, w, block_index, B, Hl, Wl, n_t, st);
   LevelW& L = u.levels[w.level];
   const int C = w.C, HW = Hl * Wl, M = B * HW;
   const int* pl = u.plan_dev + 4 * block_index;     // {skip, e1, e2, -}: every kernel of the block reads it on the device
@@ -705,6 +712,50 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
   if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
+  return LDMB_OK;
+}
+
+// One SwinBlock with PER-IMAGE stochastic-depth / expert decisions (the reference's batch-1 loops, sample_ldm.py:71-72,
+// draw them per image).  Exact, with dense kernels only: all five ReGLU experts are evaluated, the two an image did
+// not draw are zeroed in h before the c-projection, the c biases are added per image, and the rows of images that
+// skip the block are saved before it and restored after it.
+int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, int Wl, int n_t, cudaStream_t st) {
+  UNetState& u = h->unet;
+  LevelW& L = u.levels[w.level];
+  const int C = w.C, HW = Hl * Wl, M = B * HW;
+  const int* pimg = u.plan_img_dev + (size_t)block_index * B;
+  float* x = static_cast<float*>(L.xs.p);
+  const float* film = static_cast<const float*>(L.film.p) + (size_t)w.lb * n_t * HW * 2 * C;
+  int rc;
+  CKL(launch_skip_rows(x, static_cast<float*>(u.backup.p), pimg, M, HW, C, false, st));
+  CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
+       launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, nullptr, st));
+  if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, nullptr, st, false))) return rc;
+  const int ldh = 6 * C;                                   // hbuf row: [h_general | h_e0 .. h_e3 | attention]
+  if (w.attn) {
+    GemmDesc d = gd();
+    d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
+    d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE;
+    if ((rc = gemm(h, d, st, PK_QKV))) return rc;
+    const bool global = Hl <= kWindow && Wl <= kWindow;
+    CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
+         launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 5LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
+                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, nullptr, st));
+  }
+  {
+    GemmDesc d = gd();                                     // all five experts: [M,C] . [C, 10C], ReGLU gate -> h [M, 5C]
+    d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
+    d.M = M; d.N = 10 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
+    if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
+    CKL(launch_mask_experts(u.hbuf.p, ldh, h->bf16(), pimg, M, HW, C, st));
+    GemmDesc c = gd();                                     // x += [h | att] . [Wc_g | Wc_0..3 | W_out]^T, biases per image below
+    c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = nullptr; c.out = x; c.ldo = C;
+    c.M = M; c.N = C; c.K = (w.attn ? 6 : 5) * C; c.epi = EPI_ACCUM_F32;
+    c.sel = 3; c.sel_span = C; c.sel_stride = C;
+    if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
+    CKL(launch_rows_bias(x, w.b_c, pimg, M, HW, C, w.attn, st));
+  }
+  CKL(launch_skip_rows(x, static_cast<float*>(u.backup.p), pimg, M, HW, C, true, st));
   return LDMB_OK;
 }
 
@@ -796,10 +847,11 @@ extern "C" int ldmb_set_use_graphs(ldmb_handle* h, int on) {
   return LDMB_OK;
 }
 
-extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
-                                 const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
-                                 const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
-  if (!h || !x_dev || !out_dev || !t_index || !plan) return LDMB_ERR_INVALID;
+static int unet_forward_impl(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
+                             const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
+                             const int32_t* plan_img, const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
+  if (!h || !x_dev || !out_dev || !t_index || (!plan && !plan_img)) return LDMB_ERR_INVALID;
+  const bool per_image = plan_img != nullptr;
   const bool pre = te_host == nullptr;      // FiLM tables of the n_t timesteps were precomputed (ldmb_unet_precompute_film)
   UNetState& u = h->unet;
   if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
@@ -818,12 +870,16 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   if (pre && (u.film_nt != n_t || u.film_Hs != Hs || u.film_Ws != Ws))
     return fail(h, LDMB_ERR_STATE, "te_host == NULL needs ldmb_unet_precompute_film for %d timesteps at this resolution", n_t);
   if (!pre) u.film_nt = 0;                   // this call overwrites the FiLM workspace
-  for (int b = 0; b < nblk; ++b)
+  for (int b = 0; b < nblk && !per_image; ++b)
     if (!plan[3 * b] && (plan[3 * b + 1] < 0 || plan[3 * b + 1] >= kExperts || plan[3 * b + 2] < 0 || plan[3 * b + 2] >= kExperts))
       return fail(h, LDMB_ERR_INVALID, "plan: expert index out of range");
+  for (long long i = 0; per_image && i < (long long)nblk * B; ++i)
+    if (!plan_img[3 * i] && (plan_img[3 * i + 1] < 0 || plan_img[3 * i + 1] >= kExperts || plan_img[3 * i + 2] < 0 ||
+                             plan_img[3 * i + 2] >= kExperts || plan_img[3 * i + 1] == plan_img[3 * i + 2]))
+      return fail(h, LDMB_ERR_INVALID, "per-image plan: expert indices out of range or equal");
   if (coef && coef->sigma != 0.f && !noise_dev) return fail(h, LDMB_ERR_INVALID, "sigma != 0 needs a noise tensor");
   int rc;
-  if ((rc = unet_reserve(h, B, Hs, Ws, n_t))) return rc;
+  if ((rc = unet_reserve(h, B, Hs, Ws, n_t, per_image))) return rc;
   for (int l = 0; l < S; ++l)
     if (u.levels[l].peH != (Hs >> l) || u.levels[l].peW != (Ws >> l) || !u.levels[l].pe.p)
       return fail(h, LDMB_ERR_STATE, "position table of level %d not set for %dx%d", l, Hs >> l, Ws >> l);
@@ -833,13 +889,15 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   const size_t off_plan = al(sizeof(StepParams));
   const size_t off_tidx = off_plan + al((size_t)nblk * 16);
   size_t off_te[LDMB_MAX_LEVELS];
-  size_t total = off_tidx + al((size_t)B * 4);
+  const size_t off_pimg = off_tidx + al((size_t)B * 4);
+  size_t total = off_pimg + (per_image ? al((size_t)nblk * B * 4) : 0);
   for (int l = 0; l < S; ++l) { off_te[l] = total; total += pre ? 0 : al((size_t)n_t * u.levels[l].C * 4); }
   if ((rc = ensure(h, u.stepbuf, total))) return rc;
   char* sb = static_cast<char*>(u.stepbuf.p);
   u.sp_dev = reinterpret_cast<const StepParams*>(sb);
   u.plan_dev = reinterpret_cast<const int*>(sb + off_plan);
   u.tindex_dev = reinterpret_cast<const int*>(sb + off_tidx);
+  u.plan_img_dev = per_image ? reinterpret_cast<const int*>(sb + off_pimg) : nullptr;
   const float* te_dev[LDMB_MAX_LEVELS];
   for (int l = 0; l < S; ++l) te_dev[l] = reinterpret_cast<const float*>(sb + off_te[l]);
 
@@ -867,7 +925,15 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   }
   memcpy(hp, &spv, sizeof(spv));
   int* hplan = reinterpret_cast<int*>(hp + off_plan);
-  for (int b = 0; b < nblk; ++b) { hplan[4 * b] = plan[3 * b]; hplan[4 * b + 1] = plan[3 * b + 1]; hplan[4 * b + 2] = plan[3 * b + 2]; hplan[4 * b + 3] = 0; }
+  for (int b = 0; b < nblk; ++b) {
+    hplan[4 * b] = per_image ? 0 : plan[3 * b]; hplan[4 * b + 1] = per_image ? 0 : plan[3 * b + 1];
+    hplan[4 * b + 2] = per_image ? 1 : plan[3 * b + 2]; hplan[4 * b + 3] = 0;
+  }
+  if (per_image) {
+    int* hp_img = reinterpret_cast<int*>(hp + off_pimg);
+    for (long long i = 0; i < (long long)nblk * B; ++i)
+      hp_img[i] = (plan_img[3 * i] ? 1 : 0) | (plan_img[3 * i + 1] << 8) | (plan_img[3 * i + 2] << 16);
+  }
   memcpy(hp + off_tidx, t_index, (size_t)B * 4);
   for (int l = 0; l < S && !pre; ++l) {
     if (!te_host[l]) return fail(h, LDMB_ERR_INVALID, "te_host[%d] is NULL", l);
@@ -883,10 +949,10 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   UNetState::GraphEntry* ge = nullptr;
   if (u.use_graphs && !h->prof_on && cap == cudaStreamCaptureStatusNone) {
     for (auto& g : u.graphs)
-      if (g.B == B && g.Hs == Hs && g.Ws == Ws && g.n_t == n_t && g.pre == (int)pre) { ge = &g; break; }
+      if (g.B == B && g.Hs == Hs && g.Ws == Ws && g.n_t == n_t && g.pre == (int)pre && g.per_image == (int)per_image) { ge = &g; break; }
     if (!ge) {
       if (u.graphs.size() >= 16) { for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec); u.graphs.clear(); }
-      u.graphs.push_back({B, Hs, Ws, n_t, (int)pre, u.ws_epoch, nullptr, 0, 0});
+      u.graphs.push_back({B, Hs, Ws, n_t, (int)pre, (int)per_image, u.ws_epoch, nullptr, 0, 0});
       ge = &u.graphs.back();
     }
     if (ge->epoch != u.ws_epoch) {     // a workspace moved since capture: the graph holds stale pointers
@@ -917,6 +983,21 @@ extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_
   }
   if (ge) ge->seen++;
   return issue_forward(h, B, Hs, Ws, n_t, te_dev, st, pre);
+}
+
+extern "C" int ldmb_unet_forward(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
+                                 const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
+                                 const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
+  if (!plan) return LDMB_ERR_INVALID;
+  return unet_forward_impl(h, x_dev, out_dev, B, H, W, t_index, n_t, te_host, plan, nullptr, coef, noise_dev, stream);
+}
+
+extern "C" int ldmb_unet_forward_per_image(ldmb_handle* h, const float* x_dev, float* out_dev, int B, int H, int W,
+                                           const int32_t* t_index, int n_t, const float* const* te_host,
+                                           const int32_t* plan_img, const ldmb_ddim_coef* coef, const float* noise_dev,
+                                           void* stream) {
+  if (!plan_img) return LDMB_ERR_INVALID;
+  return unet_forward_impl(h, x_dev, out_dev, B, H, W, t_index, n_t, te_host, nullptr, plan_img, coef, noise_dev, stream);
 }
 
 extern "C" int ldmb_unet_precompute_film(ldmb_handle* h, int H, int W, int n_t, const float* const* te_host, void* stream) {

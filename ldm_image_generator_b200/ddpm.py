@@ -118,3 +118,49 @@ class DDPM(nn.Module):
             bar.update(1)
         bar.close()
         return x
+
+    @torch.no_grad()
+    def sample_independent(self, num_images, x_shape=(1, 3, 64, 64), seeds=None, num_steps=20, use_autocast=True,
+                           schedule="linear", eta=0, progress=False):
+        """``[self.sample(x_shape, seed=seeds[i] if seeds else None, ...) for i in range(num_images)]`` -- the loop of
+        the reference's sample scripts (sample_ldm.py:71-72 with seeds=None, sample_ddpm.py:35-36 with seeds=range(n);
+        ``x_shape[0]`` must be 1 as there) -- computed as ONE batch: Python's ``random`` and torch's generator are
+        consumed image by image in the order those calls would consume them (x_T, then per step the block decisions
+        and the noise draw), then all images are denoised together with per-image plans (ldmb_unet_forward_per_image).
+        Returns ``[num_images, *x_shape[1:]]``."""
+        if x_shape[0] != 1:
+            raise ValueError("sample_independent emulates batch-1 calls: x_shape[0] must be 1")
+        if not isinstance(self.model, UNet):
+            raise TypeError("sample_independent needs the fused UNet")
+        device = next(self.model.parameters()).device
+        pairs = self.timesteps(num_steps, schedule)
+        x_T, plans, noises = [], [], []
+        for i in range(num_images):
+            if seeds is not None and seeds[i] != None:  # noqa: E711
+                random.seed(seeds[i])
+                torch.manual_seed(seeds[i])
+                torch.cuda.manual_seed(seeds[i])
+            x_T.append(torch.randn(*x_shape, device=device))
+            per_step, per_noise = [], []
+            for _ in pairs:
+                per_step.append(self.model.draw_plan())         # ddpm.py:78 -> unet.py:39, modules.py:35
+                e = torch.randn(*x_shape, device=device)         # ddpm.py:80: drawn every step
+                if eta != 0:
+                    per_noise.append(e)
+            plans.append(per_step)
+            noises.append(per_noise)
+        x = torch.cat(x_T, dim=0)
+        alpha_cum = torch.cumprod((1 - self.beta), dim=0)
+        chunk = self.model.film_chunk(x.shape[2] // self.model.stem_size, x.shape[3] // self.model.stem_size)
+        bar = tqdm(total=len(pairs), disable=not progress)
+        for k, (t, t_next) in enumerate(pairs):
+            t, t_next = int(t), int(t_next)
+            if k % chunk == 0:
+                self.model.precompute_film(x, [int(p[0]) for p in pairs[k:k + chunk]])
+            co, _ = self.ddim_scalars(alpha_cum, t, t_next, eta)
+            e = torch.cat([noises[i][k] for i in range(num_images)], dim=0) if co.sigma != 0.0 else None
+            x = self.model.denoise_step(x, t, co, e, check_params=(k == 0), plans_per_image=[plans[i][k] for i in range(num_images)])
+            bar.update(1)
+        bar.close()
+        return x
+

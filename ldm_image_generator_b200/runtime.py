@@ -159,7 +159,8 @@ class Handle:
         self.check(self.lib.ldmb_unet_precompute_film(self.h, H, W, te_tables[0].shape[0], te_ptrs, stream_ptr(self.device)))
 
     def unet_forward(self, x: torch.Tensor, out: torch.Tensor, t_index, te_tables: Sequence[torch.Tensor], plan,
-                     coef: Optional[_lib.DdimCoef] = None, noise: Optional[torch.Tensor] = None) -> None:
+                     coef: Optional[_lib.DdimCoef] = None, noise: Optional[torch.Tensor] = None, per_image: bool = False) -> None:
+        """plan: [(skip, e1, e2)] per block, or with ``per_image`` [[(skip, e1, e2)] per image] per block."""
         B, _, H, W = x.shape
         if isinstance(te_tables, int):       # FiLM tables precomputed for this many timesteps (unet_precompute_film)
             n_t, te_ptrs = te_tables, None
@@ -167,9 +168,15 @@ class Handle:
             n_t = te_tables[0].shape[0]
             te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
         ti = (C.c_int32 * B)(*t_index)
-        flat = [int(v) for row in plan for v in row]
+        if per_image:
+            flat = [int(v) for blk in plan for row in blk for v in row]
+            if len(flat) != 3 * B * len(plan):
+                raise LdmbError("per-image plan must be [n_blocks][B][3]")
+        else:
+            flat = [int(v) for row in plan for v in row]
         pl = (C.c_int32 * len(flat))(*flat)
-        self.check(self.lib.ldmb_unet_forward(
+        fn = self.lib.ldmb_unet_forward_per_image if per_image else self.lib.ldmb_unet_forward
+        self.check(fn(
             self.h, x.data_ptr(), out.data_ptr(), B, H, W, ti, n_t, te_ptrs, pl,
             C.byref(coef) if coef is not None else None,
             noise.data_ptr() if noise is not None else None, stream_ptr(self.device)))

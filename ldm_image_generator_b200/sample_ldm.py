@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """LDM sampling CLI with the flags of the reference script (/root/reference/sample_ldm.py:11-23), running the
-UNet / DDIM / VAE-decode path in libldmb200.  Extras: ``--batch`` samples several images per call (same weights,
-shared per-step expert plan) and ``--precision`` picks bf16 (default) or the fp32 validation mode."""
+UNet / DDIM / VAE-decode path in libldmb200.  Extras: ``--batch`` denoises several images together -- with per-image
+stochastic-depth / expert decisions and per-image noise drawn in the order the reference's batch-1 loop draws them
+(DDPM.sample_independent), so the images are the ones the loop would produce; ``--shared-plan`` uses one decision per
+step for the whole batch instead (faster: one reference forward on a batch); ``--precision`` picks bf16 (default) or
+the fp32 validation mode."""
 import argparse
 import os
 import sys
@@ -25,7 +28,8 @@ def main():
     parser.add_argument('-n', '--numimages', default=1, type=int)
     parser.add_argument('-t', '--timesteps', default=20, type=int)
     parser.add_argument('--seed', default=0, type=int)
-    parser.add_argument('--batch', default=1, type=int, help="images per sample() call (reference: 1)")
+    parser.add_argument('--batch', default=1, type=int, help="images denoised together (reference: 1)")
+    parser.add_argument('--shared-plan', action='store_true', help="one stochastic-depth / expert decision per step for the whole batch")
     parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     parser.add_argument('-o', '--outdir', default='./ddpm_outputs/')
     args = parser.parse_args()
@@ -51,7 +55,10 @@ def main():
     done = 0
     while done < args.numimages:
         b = min(args.batch, args.numimages - done)
-        z = ddpm.sample((b, 8, latent, latent), seed=None, num_steps=args.timesteps, use_autocast=args.fp16)
+        if b == 1 or args.shared_plan:
+            z = ddpm.sample((b, 8, latent, latent), seed=None, num_steps=args.timesteps, use_autocast=args.fp16)
+        else:       # == [ddpm.sample((1, 8, latent, latent), ...) for _ in range(b)] of sample_ldm.py:71-72, as one batch
+            z = ddpm.sample_independent(b, (1, 8, latent, latent), seeds=None, num_steps=args.timesteps, use_autocast=args.fp16)
         imgs = decoder.decode_to_uint8(z).cpu().numpy()       # clamp, *127.5+127.5, uint8, HWC fused into the last kernel
         for k in range(b):
             Image.fromarray(imgs[k], mode='RGB').save(os.path.join(args.outdir, f"{done + k}.jpg"))

@@ -200,7 +200,9 @@ class UNet(nn.Module):
         return te
 
     def _run(self, x: torch.Tensor, t_values: Sequence[int], coef=None, noise=None, out=None, plan=None,
-             check_params: bool = True) -> torch.Tensor:
+             check_params: bool = True, plans_per_image=None) -> torch.Tensor:
+        """``plan``: one (skip, e1, e2) per block shared by the batch (one reference forward on the batch);
+        ``plans_per_image``: one such plan PER IMAGE (a batch of the reference's batch-1 forwards)."""
         runtime._require_cuda(x, "UNet input")
         p0 = next(self.parameters())
         runtime._require_cuda(p0, "UNet parameters")
@@ -221,10 +223,16 @@ class UNet(nn.Module):
                 uniq = sorted(set(int(v) for v in t_values))
                 index = {v: i for i, v in enumerate(uniq)}
                 te = self._time_tables(uniq)
-            if plan is None:
-                plan = self.draw_plan()
             if out is None:
                 out = torch.empty_like(x)
+            if plans_per_image is not None:
+                if len(plans_per_image) != B:
+                    raise RuntimeError(f"plans_per_image has {len(plans_per_image)} entries for a batch of {B}")
+                by_block = [[plans_per_image[b][k] for b in range(B)] for k in range(len(plans_per_image[0]))]
+                h.unet_forward(x, out, [index[int(v)] for v in t_values], te, by_block, coef, noise, per_image=True)
+                return out
+            if plan is None:
+                plan = self.draw_plan()
             h.unet_forward(x, out, [index[int(v)] for v in t_values], te, plan, coef, noise)
         return out
 
@@ -237,9 +245,17 @@ class UNet(nn.Module):
             t_values = t_values * x.shape[0]
         return self._run(x, t_values)
 
+    def forward_independent(self, x, time):
+        """The batch as B separate reference forwards ``UNet(x[b:b+1], time[b:b+1])`` in image order: every image draws
+        its own stochastic-depth / expert decisions from Python's ``random`` (unet.py:39, modules.py:35)."""
+        t_values = [int(v) for v in time.detach().reshape(-1).tolist()]
+        if len(t_values) == 1 and x.shape[0] > 1:
+            t_values = t_values * x.shape[0]
+        return self._run(x, t_values, plans_per_image=[self.draw_plan() for _ in range(x.shape[0])])
+
     def denoise_step(self, x: torch.Tensor, t: int, coef: "_lib.DdimCoef", noise: Optional[torch.Tensor] = None,
-                     out: Optional[torch.Tensor] = None, check_params: bool = True) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, check_params: bool = True, plans_per_image=None) -> torch.Tensor:
         """One iteration of DDPM.sample (ddpm.py:77-91): eps = UNet(x, t) and the DDIM update fused
         into the network's last kernel.  Writes into ``out`` (default: in place into ``x``)."""
         return self._run(x, [int(t)] * x.shape[0], coef=coef, noise=noise, out=x if out is None else out,
-                         check_params=check_params)
+                         check_params=check_params, plans_per_image=plans_per_image)

@@ -176,3 +176,26 @@ def test_full_size_decode_vs_oracle_and_shard_equivalence():
     assert tuple(u8.shape) == (12, 256, 256, 3)
     assert int((u8[pick].int() - R.to_uint8_image(want).int()).abs().max()) <= 3
     assert_no_fault(dec)
+
+
+def test_sample_independent_equals_the_batch1_loop():
+    """DDPM.sample_independent(n) == the reference scripts' loop of batch-1 sample() calls (sample_ddpm.py:35-36 with
+    seed=i per image; sample_ldm.py:71-72 with one seed before the loop), computed as one batch with per-image plans:
+    same Python-RNG and torch-generator consumption, same images."""
+    import random
+    d, shape = _ddpm("fp32")
+    one = (1,) + tuple(shape[1:])
+    for training in (False, True):
+        d.train(training)
+        loop = torch.cat([d.sample(one, seed=i, num_steps=5, progress=False) for i in range(3)])
+        batch = d.sample_independent(3, one, seeds=[0, 1, 2], num_steps=5)
+        assert R.rel_l2(batch.cpu(), loop.cpu()) < 2e-5, training
+        random.seed(9); torch.manual_seed(9); torch.cuda.manual_seed(9)
+        loop = torch.cat([d.sample(one, seed=None, num_steps=4, eta=0.3, progress=False) for _ in range(3)])
+        tail_loop = (random.random(), float(torch.rand(1, device="cuda")))
+        random.seed(9); torch.manual_seed(9); torch.cuda.manual_seed(9)
+        batch = d.sample_independent(3, one, seeds=None, num_steps=4, eta=0.3)
+        tail_batch = (random.random(), float(torch.rand(1, device="cuda")))
+        assert R.rel_l2(batch.cpu(), loop.cpu()) < 2e-5, training
+        assert tail_loop == tail_batch                      # both RNG streams end in the same state
+    assert_no_fault(d.model)

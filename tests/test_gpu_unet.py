@@ -141,3 +141,30 @@ def test_full_size_step_vs_oracle_and_shard_equivalence():
     assert torch.equal(shards, yd)
     assert R.rel_l2(yd[pick], want) < BF16_STEP_TOL and R.rel_l2(y, yd) < 3e-3
     assert_no_fault(model)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_per_image_plans_match_batch1_forwards(precision):
+    """A batch with PER-IMAGE stochastic-depth / expert decisions (what the reference's batch-1 sample loops compute,
+    sample_ldm.py:71-72) against the oracle run image by image with that image's plan; real channel widths, attention
+    blocks, per-sample timesteps, train mode (skips).  Python's `random` is consumed in image order."""
+    cfg = R.UNetCfg(input_channels=8, stages=(2, 2), channels=(128, 256))
+    sd = R.make_unet_state(cfg, 31)
+    model = build_unet(cfg, sd, precision)
+    model.train(True)
+    B = 5
+    x = torch.randn(B, 8, 16, 16); t = torch.tensor([10, 999, 10, 500, 3])
+    nblk = len(R.block_table(cfg))
+    random.seed(77)
+    with torch.no_grad():
+        y = model.forward_independent(x.cuda(), t.cuda()).cpu()
+    after = random.getstate()
+    random.seed(77)
+    plans = [R.draw_plan(nblk, True) for _ in range(B)]
+    assert random.getstate() == after
+    assert len({tuple(p) for p in plans}) > 1 and any(e[0] for p in plans for e in p)     # plans differ, some blocks skipped
+    want = torch.cat([R.unet_forward(sd, cfg, x[b:b + 1], t[b:b + 1], plans[b]) for b in range(B)])
+    err = R.rel_l2(y, want)
+    print(f"per-image plans {precision}: rel-L2 {err:.3e}")
+    assert err < (FP32_STEP_TOL if precision == "fp32" else BF16_STEP_TOL), err
+    assert_no_fault(model)
