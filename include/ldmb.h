@@ -176,6 +176,16 @@ int ldmb_unet_forward_per_image(ldmb_handle* h, const float* x_dev, float* out_d
                                 const int32_t* plan_img, const ldmb_ddim_coef* coef, const float* noise_dev,
                                 void* stream);
 
+/* Host-only helper of the per-image path (no handle, no device work): the block decisions of n_plans consecutive
+ * reference forwards, replayed from a stream of raw MT19937 outputs exactly as CPython's `random` consumes them --
+ * per block, `random.random() <= depth_p[k]` iff training[k] (unet.py:39: two 32-bit words -> a 53-bit double), then
+ * `random.sample(experts, 2)` unless skipped (modules.py:35: _randbelow(n) then _randbelow(n-1), each
+ * getrandbits(bit_length) = word >> (32 - bits) with rejection).  raw: the next n_raw 32-bit outputs of the caller's
+ * generator; plan_out: int32 [n_plans][n_blocks][3] = (skip, e1, e2); *used = words consumed (the caller advances its
+ * generator by that many).  Returns LDMB_ERR_INVALID when raw runs out (call again with a longer stream). */
+int ldmb_host_draw_plans(const uint32_t* raw, int64_t n_raw, int n_plans, int n_blocks, const uint8_t* training,
+                         const double* depth_p, int n_experts, int32_t* plan_out, int64_t* used);
+
 /* The Encodings MLP (unet.py:18-21) of every block for ALL n_t timesteps of a sampling schedule in one batched pass
  * (its weights, 58 % of the parameters, are then streamed once per schedule instead of once per step).
  * te_host as in ldmb_unet_forward.  Valid until the next ldmb_unet_load_param / ldmb_unet_forward with te_host != NULL. */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ldmb_debug_tc_trace": (C.c_int, [_H, C.c_int, _I64P, C.c_int]),
     "ldmb_unet_forward_per_image": (C.c_int, [_H, _P, _P, C.c_int, C.c_int, C.c_int, _I32P, C.c_int, C.POINTER(_P), _I32P,
                                               C.POINTER(DdimCoef), _P, _P]),
+    "ldmb_host_draw_plans": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P, _I64P]),
     "ldmb_unet_precompute_film": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.POINTER(_P), _P]),
     "ldmb_set_deterministic": (C.c_int, [_H, C.c_int]),
     "ldmb_debug_skip_classes": (C.c_int, [_H, C.c_uint32]),

@@ -833,6 +833,44 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
 
 }  // namespace
 
+extern "C" int ldmb_host_draw_plans(const uint32_t* raw, int64_t n_raw, int n_plans, int n_blocks, const uint8_t* training,
+                                    const double* depth_p, int n_experts, int32_t* plan_out, int64_t* used) {
+  if (!raw || !training || !depth_p || !plan_out || !used || n_plans < 0 || n_blocks <= 0 || n_experts < 2 || n_experts > 21)
+    return LDMB_ERR_INVALID;                      // random.sample switches to its set-based path above 21 items
+  int bits[2];
+  for (int i = 0; i < 2; ++i) {
+    int n = n_experts - i, b = 0;
+    while (n >> b) ++b;                            // int.bit_length()
+    bits[i] = b;
+  }
+  int64_t pos = 0;
+  for (int p = 0; p < n_plans; ++p)
+    for (int k = 0; k < n_blocks; ++k) {
+      int32_t* o = plan_out + ((size_t)p * n_blocks + k) * 3;
+      o[0] = o[1] = o[2] = 0;
+      if (training[k]) {
+        if (pos + 2 > n_raw) return LDMB_ERR_INVALID;
+        const double a = (double)(raw[pos] >> 5), b = (double)(raw[pos + 1] >> 6);
+        pos += 2;
+        if ((a * 67108864.0 + b) * (1.0 / 9007199254740992.0) <= depth_p[k]) { o[0] = 1; continue; }
+      }
+      int j[2];
+      for (int i = 0; i < 2; ++i) {
+        uint32_t r;
+        do {
+          if (pos >= n_raw) return LDMB_ERR_INVALID;
+          r = raw[pos++] >> (32 - bits[i]);
+        } while (r >= (uint32_t)(n_experts - i));
+        j[i] = (int)r;
+      }
+      // pool = [0..n); first = pool[j0]; pool[j0] = pool[n-1]; second = pool[j1]
+      o[1] = j[0];
+      o[2] = j[1] == j[0] ? n_experts - 1 : j[1];
+    }
+  *used = pos;
+  return LDMB_OK;
+}
+
 extern "C" int ldmb_set_deterministic(ldmb_handle* h, int on) {
   if (!h) return LDMB_ERR_INVALID;
   tc_set_splitk(h->tc, on == 0);

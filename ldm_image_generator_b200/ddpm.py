@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import random
 
+import numpy as np
 import torch
 import torch.nn as nn
 from tqdm import tqdm
@@ -26,6 +27,31 @@ def _default_model() -> UNet:
     if _shared_default_unet is None:
         _shared_default_unet = UNet()
     return _shared_default_unet
+
+
+def _skip_randn(shape, device, count: int) -> None:
+    """Leave torch's generator of ``device`` where ``count`` calls of ``torch.randn(*shape, device=device)`` leave it.
+    A CUDA (Philox) generator advances by a fixed offset per call of a given size: one real draw measures it, the rest
+    is one ``set_offset``.  Anything else (CPU generator, no offset API) just draws."""
+    if count <= 0:
+        return
+    gen = None
+    if torch.device(device).type == "cuda":
+        idx = torch.device(device).index
+        gen = torch.cuda.default_generators[torch.cuda.current_device() if idx is None else idx]
+    done = 0
+    try:
+        before = gen.get_offset()
+        torch.randn(*shape, device=device)
+        done = 1
+        step = gen.get_offset() - before
+        if step > 0:
+            gen.set_offset(gen.get_offset() + step * (count - 1))
+            return
+    except (AttributeError, RuntimeError):
+        pass
+    for _ in range(count - done):
+        torch.randn(*shape, device=device)
 
 
 class DDPM(nn.Module):
@@ -134,21 +160,23 @@ class DDPM(nn.Module):
             raise TypeError("sample_independent needs the fused UNet")
         device = next(self.model.parameters()).device
         pairs = self.timesteps(num_steps, schedule)
+        n_steps = len(pairs)
         x_T, plans, noises = [], [], []
+        if seeds is None:           # one uninterrupted Python-RNG stream: image-major, exactly the loop's order
+            plans = self.model.draw_plans(num_images * n_steps).reshape(num_images, n_steps, -1, 3)
         for i in range(num_images):
-            if seeds is not None and seeds[i] != None:  # noqa: E711
-                random.seed(seeds[i])
-                torch.manual_seed(seeds[i])
-                torch.cuda.manual_seed(seeds[i])
+            if seeds is not None:
+                if seeds[i] != None:  # noqa: E711
+                    random.seed(seeds[i])
+                    torch.manual_seed(seeds[i])
+                    torch.cuda.manual_seed(seeds[i])
+                plans.append(self.model.draw_plans(n_steps))     # ddpm.py:78 -> unet.py:39, modules.py:35
             x_T.append(torch.randn(*x_shape, device=device))
-            per_step, per_noise = [], []
-            for _ in pairs:
-                per_step.append(self.model.draw_plan())         # ddpm.py:78 -> unet.py:39, modules.py:35
-                e = torch.randn(*x_shape, device=device)         # ddpm.py:80: drawn every step
-                if eta != 0:
-                    per_noise.append(e)
-            plans.append(per_step)
-            noises.append(per_noise)
+            if eta != 0:
+                noises.append([torch.randn(*x_shape, device=device) for _ in pairs])
+            else:                   # ddpm.py:80 draws the noise every step even when sigma == 0: consume, do not keep
+                _skip_randn(x_shape, device, n_steps)
+        plans = np.asarray(plans, dtype=np.int32).reshape(num_images, n_steps, -1, 3)
         x = torch.cat(x_T, dim=0)
         alpha_cum = torch.cumprod((1 - self.beta), dim=0)
         chunk = self.model.film_chunk(x.shape[2] // self.model.stem_size, x.shape[3] // self.model.stem_size)
@@ -159,7 +187,7 @@ class DDPM(nn.Module):
                 self.model.precompute_film(x, [int(p[0]) for p in pairs[k:k + chunk]])
             co, _ = self.ddim_scalars(alpha_cum, t, t_next, eta)
             e = torch.cat([noises[i][k] for i in range(num_images)], dim=0) if co.sigma != 0.0 else None
-            x = self.model.denoise_step(x, t, co, e, check_params=(k == 0), plans_per_image=[plans[i][k] for i in range(num_images)])
+            x = self.model.denoise_step(x, t, co, e, check_params=(k == 0), plans_per_image=plans[:, k])
             bar.update(1)
         bar.close()
         return x

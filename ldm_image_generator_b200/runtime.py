@@ -9,6 +9,7 @@ import ctypes as C
 import os
 from typing import Dict, Iterable, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -169,12 +170,13 @@ class Handle:
             te_ptrs = (C.c_void_p * len(te_tables))(*[t.data_ptr() for t in te_tables])
         ti = (C.c_int32 * B)(*t_index)
         if per_image:
-            flat = [int(v) for blk in plan for row in blk for v in row]
-            if len(flat) != 3 * B * len(plan):
+            keep = np.ascontiguousarray(np.asarray(plan, dtype=np.int32))
+            if keep.ndim != 3 or keep.shape[1] != B or keep.shape[2] != 3:
                 raise LdmbError("per-image plan must be [n_blocks][B][3]")
+            pl = keep.ctypes.data_as(C.POINTER(C.c_int32))
         else:
             flat = [int(v) for row in plan for v in row]
-        pl = (C.c_int32 * len(flat))(*flat)
+            pl = (C.c_int32 * len(flat))(*flat)
         fn = self.lib.ldmb_unet_forward_per_image if per_image else self.lib.ldmb_unet_forward
         self.check(fn(
             self.h, x.data_ptr(), out.data_ptr(), B, H, W, ti, n_t, te_ptrs, pl,

@@ -96,3 +96,30 @@ def test_host_plan_and_tables_match_oracle():
     assert torch.equal(position_table(128, 32, 32), R.position_table(128, 32, 32))
     t = torch.tensor([0, 20, 999])
     assert torch.equal(time_table(256, t), R.time_table(256, t))
+
+
+def test_plan_replay_in_c_consumes_python_random_exactly():
+    """UNet.draw_plans(n) (ldmb_host_draw_plans replaying the raw MT19937 stream: the per-image sampler's images x steps
+    decisions) == n calls of draw_plan() == the oracle's, with `random` left in the same state; mixed train/eval blocks,
+    a generator position in the middle of its 624-word block, and a stream long enough to cross regenerations."""
+    import random
+    import numpy as np
+    from ldm_image_generator_b200 import UNet
+    from oracle import restate as R
+    m = UNet(8, [2, 3], [32, 64])
+    nblk = len(m.blocks_in_execution_order())
+    for mode in ("eval", "train", "mixed"):
+        m.train(mode != "eval")
+        if mode == "mixed":
+            for b in m.blocks_in_execution_order()[::2]:
+                b.eval()
+        for seed, n in ((0, 1), (7, 300)):
+            random.seed(seed); [random.random() for _ in range(seed)]
+            fast = m.draw_plans(n); end = random.getstate()
+            random.seed(seed); [random.random() for _ in range(seed)]
+            slow = np.array([m.draw_plan() for _ in range(n)], dtype=np.int32)
+            assert UNet._replay_checked is True
+            assert fast.shape == (n, nblk, 3) and np.array_equal(fast, slow) and random.getstate() == end
+            if mode != "mixed":
+                random.seed(seed); [random.random() for _ in range(seed)]
+                assert [tuple(p) for p in fast[-1].tolist()] == [R.draw_plan(nblk, mode == "train") for _ in range(n)][-1]

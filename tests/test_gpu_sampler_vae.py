@@ -188,7 +188,9 @@ def test_sample_independent_equals_the_batch1_loop():
     for training in (False, True):
         d.train(training)
         loop = torch.cat([d.sample(one, seed=i, num_steps=5, progress=False) for i in range(3)])
+        tail_loop = (random.random(), float(torch.rand(1, device="cuda")))
         batch = d.sample_independent(3, one, seeds=[0, 1, 2], num_steps=5)
+        assert tail_loop == (random.random(), float(torch.rand(1, device="cuda")))    # eta == 0: noise draws skipped by offset
         assert R.rel_l2(batch.cpu(), loop.cpu()) < 2e-5, training
         random.seed(9); torch.manual_seed(9); torch.cuda.manual_seed(9)
         loop = torch.cat([d.sample(one, seed=None, num_steps=4, eta=0.3, progress=False) for _ in range(3)])

@@ -16,3 +16,18 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(4): d2.sample((1, 8, 32, 32), num_steps=50, progress=False)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 4
 print(f"batch-1 loop (the reference scripts' structure, this library): {dt * 1e3:7.1f} ms per latent -> {1 / dt:6.1f} latents/s")
+# device time of one per-image step against one shared-plan step (same batch, same t), per profile class
+import numpy as np
+x = torch.randn(64, 8, 32, 32, device="cuda")
+u.precompute_film(x, [500])
+co, _ = d.ddim_scalars(torch.cumprod(1 - d.beta, dim=0), 500, 480, 0)
+plans = u.draw_plans(64)
+shared = u.draw_plan()
+for name, kw in (("shared-plan step", dict(plan=shared)), ("per-image step", dict(plans_per_image=plans))):
+    for _ in range(3): u._run(x, [500] * 64, coef=co, out=x.clone(), check_params=False, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): u._run(x, [500] * 64, coef=co, out=x.clone(), check_params=False, **kw)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / 20:6.3f} ms on the device")
+t0 = time.perf_counter(); u.draw_plans(64 * 50); print(f"drawing 64 x 50 plans: {(time.perf_counter() - t0) * 1e3:.1f} ms of host time")
