@@ -42,6 +42,9 @@ struct GemmDesc {
   // slot q > 0 uses rows (1 + e_q) * sel_stride, slot 3 (attention out_proj) rows 5 * sel_stride; skip => kernel exits.
   const int* plan; int sel_stride;
   int glu_chunk;                       // EPI_REGLU: a and b columns interleaved in chunks of this many columns
+  // EPI_REGLU with per-image expert decisions: output column block q = j / mask_span (q >= 1: expert q - 1) of row m is
+  // written as zero unless the image m / mask_rows drew that expert (word per image: skip | e1 << 8 | e2 << 16)
+  const int* mask_plan; int mask_rows, mask_span;
   // grid.z batching (grouped convolution groups, per-block FiLM projections)
   int batch; long long a_koff_b, w_row_b, out_off_b, bias_off_b;
   int ctH, ctW, ctC;                   // EPI_CONVT: input height, width, output channels
@@ -53,6 +56,14 @@ struct StepParams {
   float c_eps_in, c_div, c_x0, c_eps_out, sigma;
   int final_step, ddim_enabled;
 };
+
+// Does row m of a per-image-masked ReGLU output keep column j?  (modules.py:35-36: general + the two drawn experts)
+__device__ __forceinline__ bool expert_kept(const GemmDesc& d, int m, int j) {
+  const int q = j / d.mask_span;
+  if (q == 0) return true;
+  const int w = d.mask_plan[(m < d.M ? m : d.M - 1) / d.mask_rows];
+  return q - 1 == ((w >> 8) & 0xff) || q - 1 == ((w >> 16) & 0xff);
+}
 
 // Resolve the device-side plan into sel_rows; returns true when the block is skipped (stochastic depth, unet.py:39-40).
 __device__ __forceinline__ bool resolve_plan(GemmDesc& d) {

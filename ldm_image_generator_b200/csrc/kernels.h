@@ -30,7 +30,9 @@ cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, con
 // w_c [w_c_rows >= 5C, C]).  plan: {skip, e1, e2, -} on the device, or NULL to use e1 / e2.
 bool mlp_fused_supported(int M, int C);
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
-                             float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, cudaStream_t st);
+                             float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
+                             cudaStream_t st);
+bool mlp_fused_per_image_supported(int M, int C, int rows_per_image);
 
 // Dense 3x3 conv with 64 input and 64 output channels through the same halo-patch kernel (VAE level at full resolution):
 // out bf16 [B,H,W,64] = act(conv(in) + bias) (+ res), act(v) = max(v,0) + slope*min(v,0); w [64][9*64] tap-major.
@@ -75,9 +77,9 @@ cudaError_t launch_final(const float* x, const float* w, const float* bias, cons
                          int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
 
 // ---- per-image plans (plan word per image: skip | e1 << 8 | e2 << 16; see kernels_simt.cu)
-cudaError_t launch_mask_experts(void* h, long long ldh, bool is_bf16, const int* plan_img, int M, int HW, int C, cudaStream_t st);
-cudaError_t launch_rows_bias(float* x, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn, cudaStream_t st);
-cudaError_t launch_skip_rows(float* x, float* backup, const int* plan_img, int M, int HW, int C, bool restore, cudaStream_t st);
+cudaError_t launch_rows_enter(float* x, float* backup, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn,
+                              cudaStream_t st);
+cudaError_t launch_rows_leave(float* x, const float* backup, const int* plan_img, int M, int HW, int C, cudaStream_t st);
 
 // ---- VAE pieces
 // 1x1 conv from an NCHW fp32 tensor with few channels (latent 8 / RGB 3) into NHWC T

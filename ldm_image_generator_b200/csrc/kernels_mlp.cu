@@ -41,7 +41,7 @@ template <int C, int CG> struct MlpCfg {
   static constexpr int SLAB_BYTES = 32 * 128;              // epilogue-2 staging aliases the (then idle) h ring
   static constexpr int TILE_BYTES = A1_BUFS * A1_BYTES + W1S * W1_BYTES + HS * (W2_BYTES + H_BYTES);
   static constexpr int BAR_BYTES = 512;
-  static constexpr int BIAS_FLOATS = 3 * 2 * C + C;
+  static constexpr int BIAS_FLOATS = 5 * 2 * C + 2 * C;    // a|b biases of all five experts + the tile's summed c biases (x2)
   static constexpr int SMEM_BYTES = 1024 + TILE_BYTES + BAR_BYTES + BIAS_FLOATS * 4;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(W1_BYTES % 1024 == 0 && W2_BYTES % 1024 == 0, "1024-byte aligned tiles");
@@ -53,6 +53,7 @@ template <int C, int CG> struct MlpCfg {
 struct MlpArgs {
   const float* b_ab; const float* b_c;
   const int* plan; int e1, e2;          // plan entry {skip, e1, e2, -} of the block, or explicit experts when NULL
+  const int* plan_img; int rows_per_image;   // per-image decisions (skip | e1 << 8 | e2 << 16 per image; a tile lies inside one image), or NULL
   int M, m_tiles;
   int dbg;                              // debug experiments: 1 = epilogue 1 idle, 2 = no GEMM2 MMAs, 4 = no GEMM1 MMAs, 8 = no x update
 };
@@ -123,8 +124,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* d2_full = d1_empty + 4;               uint64_t* d2_empty = d2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  float* sb_ab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [3][2C]
-  float* sb_c = sb_ab + 3 * 2 * C;                                                                // [C]
+  float* sb_ab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [5][2C]: every expert
+  float* sb_c = sb_ab + 5 * 2 * C;                                                                // [2][C]: this / the next tile's sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_stamp(trace, 0);
@@ -143,20 +144,35 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
   // the block's plan entry, biases and weights are older than the previous kernel: read before waiting on it
-  int e1 = a.e1, e2 = a.e2;
-  bool skip_block = false;
-  if (a.plan != nullptr) { skip_block = a.plan[0] != 0; e1 = a.plan[1]; e2 = a.plan[2]; }
-  const int slot_e[3] = {0, 1 + e1, 1 + e2};                 // row blocks of the stacked expert weights
-  for (int i = threadIdx.x; i < 3 * 2 * C; i += kThreads) sb_ab[i] = a.b_ab[slot_e[i / (2 * C)] * 2 * C + i % (2 * C)];
-  for (int i = threadIdx.x; i < C; i += kThreads) sb_c[i] = a.b_c[i] + a.b_c[slot_e[1] * C + i] + a.b_c[slot_e[2] * C + i];
+  // A tile's decisions: word = skip | e1 << 8 | e2 << 16, shared by the batch or looked up per image (per-image plans)
+  int shared_word = (a.e1 << 8) | (a.e2 << 16);
+  if (a.plan != nullptr) shared_word = (a.plan[0] != 0 ? 1 : 0) | (a.plan[1] << 8) | (a.plan[2] << 16);
+  const int t0 = blockIdx.x / CG, t_step = gridDim.x / CG;
+  const int n_tiles = (a.plan_img == nullptr && (shared_word & 1)) ? 0 : a.m_tiles;
+  const int my_tiles = t0 < n_tiles ? (n_tiles - t0 + t_step - 1) / t_step : 0;
+  auto tile_word = [&](int ti) -> int {
+    return a.plan_img != nullptr ? a.plan_img[((long long)(t0 + ti * t_step) * (128 * CG)) / a.rows_per_image] : shared_word;
+  };
+  auto next_active = [&](int ti) -> int {                    // first tile of this CTA at or after ti whose image runs the block
+    while (ti < my_tiles && (tile_word(ti) & 1)) ++ti;
+    return ti;
+  };
+  auto c_bias_sum = [&](int word, int i) -> float {          // general + e1 + e2 (modules.py:15)
+    return a.b_c[i] + a.b_c[(1 + ((word >> 8) & 0xff)) * C + i] + a.b_c[(1 + ((word >> 16) & 0xff)) * C + i];
+  };
+  for (int i = threadIdx.x; i < 5 * 2 * C; i += kThreads) sb_ab[i] = a.b_ab[i];
+  {
+    const int first = next_active(0);
+    if (first < my_tiles) {
+      const int word = tile_word(first);
+      for (int i = threadIdx.x; i < C; i += kThreads) sb_c[i] = c_bias_sum(word, i);
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = skip_block ? 0 : a.m_tiles;
-  const int t0 = blockIdx.x / CG, t_step = gridDim.x / CG;
-  const int my_tiles = t0 < n_tiles ? (n_tiles - t0 + t_step - 1) / t_step : 0;
   const bool is_producer = warp == 0 && lane == 0;
   if (threadIdx.x == 0) trace_stamp(trace, 1);
   if (!is_producer) pdl_wait();
@@ -165,36 +181,40 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // ===================================================== TMA producer
     if (lane == 0) {
       Ring ra, r1, r2;
-      const int total_units = my_tiles * UNITS;
-      int n1 = 0, n2 = 0;                                   // next unit (counted over all tiles of this CTA) of each weight ring
+      int n1 = 0, n2 = 0;                                   // next unit (counted over the active tiles of this CTA) of each weight ring
+      int w1_ti = next_active(0), w2_ti = w1_ti;            // the tile those units belong to (its image picks the experts)
       bool ok = true;
+      auto slot_of = [&](int ti, int e) -> int { return e == 0 ? 0 : 1 + ((tile_word(ti) >> (8 * e)) & 0xff); };
       auto issue_w1 = [&]() {
         const int u = n1 % UNITS, e = u / NKB, j = u % NKB;
         if (!wait_bar(&g1_done[r1.i], r1.ph ^ 1, s_abort, fault, 22)) { ok = false; return; }
         if (leader) ptx::mbar_arrive_expect_tx(&w1_full[r1.i], Cfg::W1_BYTES * CG);
-        const int row = slot_e[e] * 2 * C + j * 128 + (int)rank * Cfg::B1_ROWS;
+        const int row = slot_of(w1_ti, e) * 2 * C + j * 128 + (int)rank * Cfg::B1_ROWS;
         for (int kb = 0; kb < NKB; ++kb) {
           uint8_t* dst = w1 + r1.i * Cfg::W1_BYTES + kb * (Cfg::B1_ROWS * 128);
           if (CG == 2) ptx::tma_load_2d_2sm(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
           else ptx::tma_load_2d(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
         }
-        r1.next(W1S); ++n1;
+        r1.next(W1S);
+        if (++n1 % UNITS == 0) w1_ti = next_active(w1_ti + 1);
       };
       auto issue_w2 = [&]() {
         const int u = n2 % UNITS, e = u / NKB, j = u % NKB;
         if (!wait_bar(&g2_done[r2.i], r2.ph ^ 1, s_abort, fault, 23)) { ok = false; return; }
         if (leader) ptx::mbar_arrive_expect_tx(&w2_full[r2.i], Cfg::W2_BYTES * CG);
-        const int row = slot_e[e] * C + (int)rank * Cfg::B2_ROWS;
+        const int row = slot_of(w2_ti, e) * C + (int)rank * Cfg::B2_ROWS;
         if (CG == 2) ptx::tma_load_2d_2sm(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
         else ptx::tma_load_2d(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
-        r2.next(HS); ++n2;
+        r2.next(HS);
+        if (++n2 % UNITS == 0) w2_ti = next_active(w2_ti + 1);
       };
       // fill both weight rings while the previous kernel is still draining; only the xm tiles wait for it
-      while (ok && n1 < total_units && n1 < W1S) issue_w1();
-      while (ok && n2 < total_units && n2 < HS) issue_w2();
+      while (ok && w1_ti < my_tiles && n1 < W1S) issue_w1();
+      while (ok && w2_ti < my_tiles && n2 < HS) issue_w2();
       pdl_wait();
       trace_stamp(trace, 2);
-      for (int ti = 0; ok && ti < my_tiles; ++ti) {
+      int ta = 0;                                           // ordinal of the tile among this CTA's active tiles
+      for (int ti = next_active(0); ok && ti < my_tiles; ti = next_active(ti + 1), ++ta) {
         const int m0 = (t0 + ti * t_step) * (128 * CG) + (int)rank * 128;
         if (!wait_bar(&a1_empty[ra.i], ra.ph ^ 1, s_abort, fault, 21)) break;
         if (leader) ptx::mbar_arrive_expect_tx(&a1_full[ra.i], Cfg::A1_BYTES * CG);
@@ -205,8 +225,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         ra.next(Cfg::A1_BUFS);
         for (int s = 0; ok && s < UNITS + LAG; ++s) {     // same order as the MMA thread consumes
-          if (s < UNITS && ti * UNITS + s >= n1) issue_w1();
-          if (ok && s >= LAG && ti * UNITS + s - LAG >= n2) issue_w2();
+          if (s < UNITS && ta * UNITS + s >= n1) issue_w1();
+          if (ok && s >= LAG && ta * UNITS + s - LAG >= n2) issue_w2();
         }
       }
     }
@@ -224,9 +244,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       Ring ra, r1, r2, rd1, rd2;
       const uint32_t d2 = tmem_base + Cfg::D2_COL;
       bool ok = true;
-      for (int ti = 0; ok && ti < my_tiles; ++ti) {
+      bool first_tile = true;
+      for (int ti = next_active(0); ok && ti < my_tiles; ti = next_active(ti + 1)) {
         if (!wait_bar(&a1_full[ra.i], ra.ph, s_abort, fault, 24)) break;
-        if (ti == 0) trace_stamp(trace, 3);
+        if (first_tile) trace_stamp(trace, 3);
         ptx::tc_fence_after();
         const uint32_t a1_addr = ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES);
         for (int s = 0; ok && s < UNITS + LAG; ++s) {
@@ -269,7 +290,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         commit(d2_full);
         rd2.next(1);
         ra.next(Cfg::A1_BUFS);
-        if (ti == 0) trace_stamp(trace, 4);
+        if (first_tile) trace_stamp(trace, 4);
+        first_tile = false;
       }
       trace_stamp(trace, 5);
     }
@@ -283,12 +305,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     auto arrive = [&](uint64_t* bar) { if (CG == 2) ptx::mbar_arrive_leader(bar); else ptx::mbar_arrive(bar); };
     Ring re1, rh, rd1, rd2;
     bool ok = true;
-    for (int ti = 0; ok && ti < my_tiles; ++ti) {
+    int ta = 0;
+    for (int ti = next_active(0); ok && ti < my_tiles; ++ta) {
       const int m0 = (t0 + ti * t_step) * (128 * CG) + (int)rank * 128;
+      const int word = tile_word(ti);
+      const int slot_e[3] = {0, 1 + ((word >> 8) & 0xff), 1 + ((word >> 16) & 0xff)};   // row blocks of the stacked expert biases
+      const int ti_next = next_active(ti + 1);
+      if (ti_next < my_tiles && (int)threadIdx.x - 64 < C)      // the next tile's c biases: visible after this tile's closing barrier
+        sb_c[((ta + 1) & 1) * C + threadIdx.x - 64] = c_bias_sum(tile_word(ti_next), threadIdx.x - 64);
+      const float* sbc = sb_c + (ta & 1) * C;
       for (int u = 0; u < UNITS; ++u) {
-        const float* sb = sb_ab + (u / NKB) * 2 * C + (u % NKB) * 128;     // [64 a-biases | 64 b-biases] of this unit
+        const float* sb = sb_ab + slot_e[u / NKB] * 2 * C + (u % NKB) * 128;     // [64 a-biases | 64 b-biases] of this unit
         if (!wait_bar(&g1_done[re1.i], re1.ph, s_abort, fault, 30)) { ok = false; break; }
-        if (threadIdx.x == 64 && ti == 0 && u == 0) trace_stamp(trace, 6);
+        if (threadIdx.x == 64 && ta == 0 && u == 0) trace_stamp(trace, 6);
         if (!wait_bar(&g2_done[rh.i], rh.ph ^ 1, s_abort, fault, 31)) { ok = false; break; }   // h slot free
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + lane_off + rd1.i * 128;
@@ -343,10 +372,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
 #pragma unroll
         for (int p = 0; p < 8; ++p)
-          ptx::st_shared_v4(srow + ((p ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * p]) + sb_c[c0 + 4 * p]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 1]) + sb_c[c0 + 4 * p + 1]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 2]) + sb_c[c0 + 4 * p + 2]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 3]) + sb_c[c0 + 4 * p + 3]));
+          ptx::st_shared_v4(srow + ((p ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * p]) + sbc[c0 + 4 * p]),
+                            __float_as_uint(__uint_as_float(r[4 * p + 1]) + sbc[c0 + 4 * p + 1]),
+                            __float_as_uint(__uint_as_float(r[4 * p + 2]) + sbc[c0 + 4 * p + 2]),
+                            __float_as_uint(__uint_as_float(r[4 * p + 3]) + sbc[c0 + 4 * p + 3]));
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !(a.dbg & 8)) { ptx::tma_reduce_add_2d(&tmO, slab, c0, orow); ptx::bulk_commit(); }
@@ -360,7 +389,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // every warp's reduce has read its slab before ANY warp writes h rows again (slabs and h rows of different warps overlap)
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       rd2.next(1);
-      if (threadIdx.x == 64 && ti == 0) trace_stamp(trace, 7);
+      if (threadIdx.x == 64 && ta == 0) trace_stamp(trace, 7);
+      ti = ti_next;
     }
     if (lane == 0) ptx::bulk_wait_read<0>();                  // smem read by the reduces; the writes complete with the grid
     __syncwarp();
@@ -401,15 +431,36 @@ static int g_mlp_mode = getenv("LDMB_MLP_FUSED") ? atoi(getenv("LDMB_MLP_FUSED")
 
 bool mlp_fused_supported(int M, int C) { return g_mlp_mode != 0 && (C == 128 || C == 256) && M >= 1; }
 
+// CTAs of a cluster: pairs, except where a lone 128-row tile (C = 128) or -- with per-image decisions -- an image of an odd
+// number of 128-row tiles needs the single-CTA variant (C = 128 only).  0 = this shape cannot run fused.
+static int mlp_cta_group(int M, int C, int rows_per_image) {
+  int cg = (g_mlp_mode == 2 && (M > 128 || C == 256)) ? 2 : 1;   // a lone tile of C = 256 still runs as a pair (rows >= M: zero-filled / clipped)
+  if (rows_per_image > 0) {                                     // a tile must lie inside one image
+    if (rows_per_image % 128 != 0) return 0;
+    if (rows_per_image % (128 * cg) != 0) cg = 1;
+  }
+  if (cg == 1 && C == 256) return 0;                            // the single-CTA variant exists for C = 128 only
+  return cg;
+}
+
+bool mlp_fused_per_image_supported(int M, int C, int rows_per_image) {
+  return mlp_fused_supported(M, C) && rows_per_image > 0 && M % rows_per_image == 0 && mlp_cta_group(M, C, rows_per_image) != 0;
+}
+
 // x fp32 [M,C] += sum_e c_e(a_e(xm) * relu(b_e(xm))) over {general, e1, e2}; xm bf16 [M,C];
+// plan_img != NULL: per-image decisions (word per image: skip | e1 << 8 | e2 << 16), rows_per_image = H*W: each tile
+// resolves its own image's experts, tiles of images that skip the block do nothing.
 // w_ab bf16 [5*2C, C] (per expert: a|b rows interleaved in chunks of 64), b_ab fp32 [5*2C]; w_c bf16 [>=5C, C], b_c fp32 [>=5C].
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
-                             float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, cudaStream_t st) {
+                             float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
+                             cudaStream_t st) {
   if (!mlp_fused_supported(M, C)) return cudaErrorNotSupported;
-  const int cg = (g_mlp_mode == 2 && (M > 128 || C == 256)) ? 2 : 1;   // a lone 128-row tile of C = 256 still runs as a pair (rows >= M are out of bounds: zero-filled / clipped)
-  if (cg == 1 && C == 256) return cudaErrorNotSupported;      // the single-CTA variant exists for C = 128 only
+  if (plan_img != nullptr && !mlp_fused_per_image_supported(M, C, rows_per_image)) return cudaErrorNotSupported;
+  const int cg = mlp_cta_group(M, C, plan_img != nullptr ? rows_per_image : 0);
+  if (cg == 0) return cudaErrorNotSupported;
   MlpArgs a;
   a.b_ab = b_ab; a.b_c = b_c; a.plan = plan; a.e1 = e1; a.e2 = e2; a.M = M;
+  a.plan_img = plan_img; a.rows_per_image = rows_per_image;
   a.m_tiles = (M + 128 * cg - 1) / (128 * cg);
   a.dbg = getenv("LDMB_MLP_DBG") ? atoi(getenv("LDMB_MLP_DBG")) : 0;
   CUtensorMap tmX, tmWab, tmWc, tmO;

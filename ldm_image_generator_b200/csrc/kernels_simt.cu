@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc dparam) {
         const int na = (j / G) * 2 * G + j % G, nb = na + G;
         const float va = acc[0][i][jj] + bias_of_col(d, z, na);
         const float vb = acc[NW - 1][i][jj] + bias_of_col(d, z, nb);
-        reinterpret_cast<T*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = from_f<T>(va * fmaxf(vb, 0.f));
+        const bool keep = d.mask_plan == nullptr || expert_kept(d, m, j);
+        reinterpret_cast<T*>(d.out)[(long long)m * d.ldo + z * d.out_off_b + j] = from_f<T>(keep ? va * fmaxf(vb, 0.f) : 0.f);
       } else {
         float v = acc[0][i][jj] + bias_of_col(d, z, j);
         if (d.epi == EPI_ACCUM_F32) {
@@ -875,29 +876,23 @@ __global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __r
 // sample_ldm.py:71-72): every image of a batch carries its own plan word  skip | e1 << 8 | e2 << 16.
 // The feed-forward then evaluates all five ReGLU experts and these kernels apply the per-image choice.
 // =====================================================================================
-// h[m, (1+e)*C .. (2+e)*C) = 0 for the two experts e the image of row m did not draw (modules.py:35-36)
-template <typename T>
-__global__ void mask_experts_kernel(T* __restrict__ h, long long ldh, const int* __restrict__ plan_img, int M, int HW, int C) {
-  pdl_wait();
-  constexpr int V = 16 / sizeof(T);
-  const int pieces = 4 * C / V;                              // 16-byte pieces of the four expert blocks of a row
-  const long long total = (long long)M * pieces;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / pieces), c = (int)(i % pieces) * V, e = c / C;
-    const int w = plan_img[m / HW], e1 = (w >> 8) & 0xff, e2 = (w >> 16) & 0xff;
-    if (e != e1 && e != e2) *reinterpret_cast<uint4*>(h + (long long)m * ldh + C + c) = make_uint4(0u, 0u, 0u, 0u);
-  }
-}
-// x[m, :] += b_c[general] + b_c[e1] + b_c[e2] (+ out_proj bias)   -- the c-projection biases of the image's experts
-__global__ void rows_bias_kernel(float* __restrict__ x, const float* __restrict__ b_c, const int* __restrict__ plan_img, int M, int HW,
-                                 int C, int attn) {
+// Per-image decisions (a batch of the reference's batch-1 forwards): rows of one SwinBlock entering / leaving it.
+// Entering (after the norm has read x): rows of images that skip the block (unet.py:39-40) are saved; the other rows get
+// the c-projection biases of their image's experts, b_c[general] + b_c[e1] + b_c[e2] (+ out_proj bias) -- the branch
+// kernels that follow only ever ADD to x, so the bias can go first.  Leaving: the saved rows are put back.
+__global__ void rows_enter_kernel(float* __restrict__ x, float* __restrict__ backup, const float* __restrict__ b_c,
+                                  const int* __restrict__ plan_img, int M, int HW, int C, int attn) {
   pdl_wait();
   const int C4 = C / 4;
   const long long total = (long long)M * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / C4), c = (int)(i % C4) * 4;
-    const int w = plan_img[m / HW], e1 = (w >> 8) & 0xff, e2 = (w >> 16) & 0xff;
-    float4 v = *reinterpret_cast<float4*>(x + (long long)m * C + c);
+    const int w = plan_img[m / HW];
+    float4* xp = reinterpret_cast<float4*>(x) + i;
+    if (w & 1) { reinterpret_cast<float4*>(backup)[i] = *xp; continue; }
+    if (b_c == nullptr) continue;
+    const int e1 = (w >> 8) & 0xff, e2 = (w >> 16) & 0xff;
+    float4 v = *xp;
     const float4 g = __ldg(reinterpret_cast<const float4*>(b_c + c));
     const float4 a = __ldg(reinterpret_cast<const float4*>(b_c + (long long)(1 + e1) * C + c));
     const float4 b = __ldg(reinterpret_cast<const float4*>(b_c + (long long)(1 + e2) * C + c));
@@ -906,21 +901,17 @@ __global__ void rows_bias_kernel(float* __restrict__ x, const float* __restrict_
       const float4 o = __ldg(reinterpret_cast<const float4*>(b_c + 5LL * C + c));
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
-    *reinterpret_cast<float4*>(x + (long long)m * C + c) = v;
+    *xp = v;
   }
 }
-// stochastic depth per image (unet.py:39-40): rows of images that skip the block are saved before it and restored after
-__global__ void skip_rows_kernel(float* __restrict__ x, float* __restrict__ backup, const int* __restrict__ plan_img, int M, int HW,
-                                 int C, int restore) {
+__global__ void rows_leave_kernel(float* __restrict__ x, const float* __restrict__ backup, const int* __restrict__ plan_img, int M,
+                                  int HW, int C) {
   pdl_wait();
   const int C4 = C / 4;
   const long long total = (long long)M * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / C4);
-    if (!(plan_img[m / HW] & 1)) continue;
-    float4* a = reinterpret_cast<float4*>(x) + i;
-    float4* b = reinterpret_cast<float4*>(backup) + i;
-    if (restore) *a = *b; else *b = *a;
+    if (plan_img[m / HW] & 1) reinterpret_cast<float4*>(x)[i] = reinterpret_cast<const float4*>(backup)[i];
   }
 }
 
@@ -1105,20 +1096,14 @@ cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_mask_experts(void* h, long long ldh, bool is_bf16, const int* plan_img, int M, int HW, int C, cudaStream_t st) {
-  if (C % 8) return cudaErrorNotSupported;
-  const long long total = (long long)M * 4 * C / (is_bf16 ? 8 : 4);
-  if (is_bf16) launch_k((mask_experts_kernel<bf16>), grid_for(total, 256), 256, 0, st, (bf16*)h, ldh, plan_img, M, HW, C);
-  else launch_k((mask_experts_kernel<float>), grid_for(total, 256), 256, 0, st, (float*)h, ldh, plan_img, M, HW, C);
+cudaError_t launch_rows_enter(float* x, float* backup, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn,
+                              cudaStream_t st) {
+  if (C % 4) return cudaErrorNotSupported;
+  launch_k((rows_enter_kernel), grid_for((long long)M * C / 4, 256), 256, 0, st, x, backup, b_c, plan_img, M, HW, C, attn ? 1 : 0);
   return cudaGetLastError();
 }
-cudaError_t launch_rows_bias(float* x, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn, cudaStream_t st) {
+cudaError_t launch_rows_leave(float* x, const float* backup, const int* plan_img, int M, int HW, int C, cudaStream_t st) {
   if (C % 4) return cudaErrorNotSupported;
-  launch_k((rows_bias_kernel), grid_for((long long)M * C / 4, 256), 256, 0, st, x, b_c, plan_img, M, HW, C, attn ? 1 : 0);
-  return cudaGetLastError();
-}
-cudaError_t launch_skip_rows(float* x, float* backup, const int* plan_img, int M, int HW, int C, bool restore, cudaStream_t st) {
-  if (C % 4) return cudaErrorNotSupported;
-  launch_k((skip_rows_kernel), grid_for((long long)M * C / 4, 256), 256, 0, st, x, backup, plan_img, M, HW, C, restore ? 1 : 0);
+  launch_k((rows_leave_kernel), grid_for((long long)M * C / 4, 256), 256, 0, st, x, backup, plan_img, M, HW, C);
   return cudaGetLastError();
 }

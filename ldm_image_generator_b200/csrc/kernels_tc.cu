@@ -316,10 +316,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
                 ptx::tmem_ld_32x32(t_row + a0 + 64 + half * 32, rb);
                 ptx::tmem_ld_wait();
+                // per-image expert decisions: the 64-column slab lies inside one expert's block
+                const bool keep = d.mask_plan == nullptr || expert_kept(d, m, (n0 + a0) >> 1);
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  v[i] = (__uint_as_float(r[i]) + sb[a0 + half * 32 + i]) *
-                         fmaxf(__uint_as_float(rb[i]) + sb[a0 + 64 + half * 32 + i], 0.f);
+                  v[i] = keep ? (__uint_as_float(r[i]) + sb[a0 + half * 32 + i]) *
+                                    fmaxf(__uint_as_float(rb[i]) + sb[a0 + 64 + half * 32 + i], 0.f)
+                              : 0.f;
               } else {
                 ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
                 ptx::tmem_ld_wait();
@@ -388,6 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row_ok) {
             const int j = (n >> 7) * 64 + (n & 127);
             bf16* o = reinterpret_cast<bf16*>(d.out) + (long long)m * d.ldo + z * d.out_off_b + j;
+            const bool keep = d.mask_plan == nullptr || expert_kept(d, m, j);
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -395,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float a1 = __uint_as_float(r[2 * i + 1]) + sb[c * 32 + 2 * i + 1];
               const float g0 = fmaxf(__uint_as_float(rb[2 * i]) + sb[c * 32 + 64 + 2 * i], 0.f);
               const float g1 = fmaxf(__uint_as_float(rb[2 * i + 1]) + sb[c * 32 + 64 + 2 * i + 1], 0.f);
-              pk[i] = pack_bf16(a0 * g0, a1 * g1);
+              pk[i] = keep ? pack_bf16(a0 * g0, a1 * g1) : 0u;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -568,6 +572,7 @@ bool tc_supported(const GemmDesc& d) {
   }
   if ((d.sel == 2 || d.sel == 3) && d.sel_span % BK) return false;
   if (d.epi == EPI_REGLU && d.glu_chunk != 64) return false;
+  if (d.mask_plan != nullptr && (d.epi != EPI_REGLU || d.mask_span % 64 != 0 || d.mask_rows <= 0)) return false;   // a 64-column slab lies in one expert
   if (d.epi == EPI_CONVT && d.ctC % 32) return false;
   if (d.epi != EPI_CONVT && (d.ldo % 8 || d.out_off_b % 8)) return false;
   if (d.res && d.ldr % 8) return false;

@@ -688,7 +688,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   if (h->bf16() && !h->force_simt && mlp_fused_supported(M, C)) {
     // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM
     CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
-         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, st));
+         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st));
     if (w.attn) {   // x += att . W_out^T + b_out   (attention.py:82 out_proj; unet.py:44,47)
       GemmDesc c = gd();
       c.A = toff(h, u.hbuf.p, 3LL * C); c.lda = ldh; c.W = toff(h, w.w_c, 5LL * C * C); c.ldw = C; c.bias = w.b_c + 5LL * C;
@@ -716,9 +716,11 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
 }
 
 // One SwinBlock with PER-IMAGE stochastic-depth / expert decisions (the reference's batch-1 loops, sample_ldm.py:71-72,
-// draw them per image).  Exact, with dense kernels only: all five ReGLU experts are evaluated, the two an image did
-// not draw are zeroed in h before the c-projection, the c biases are added per image, and the rows of images that
-// skip the block are saved before it and restored after it.
+// draw them per image).  Exact.  Where an image is a whole number of 128-row tiles (C = 128 / 256 levels) the fused
+// feed-forward kernel resolves the experts per tile and does nothing for tiles of skipped images: same work as one
+// shared plan.  Elsewhere (deep levels, 16..64 pixels per image) dense kernels: all five ReGLU experts are evaluated,
+// the two an image did not draw are written as zeros by the gate epilogue, the c-projection runs over all slots and
+// its biases are added per image.  Rows of images that skip the block are saved on entry and put back on exit.
 int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, int Wl, int n_t, cudaStream_t st) {
   UNetState& u = h->unet;
   LevelW& L = u.levels[w.level];
@@ -726,11 +728,24 @@ int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B,
   const int* pimg = u.plan_img_dev + (size_t)block_index * B;
   float* x = static_cast<float*>(L.xs.p);
   const float* film = static_cast<const float*>(L.film.p) + (size_t)w.lb * n_t * HW * 2 * C;
+  const bool fused = h->bf16() && !h->force_simt && mlp_fused_per_image_supported(M, C, HW);
   int rc;
-  CKL(launch_skip_rows(x, static_cast<float*>(u.backup.p), pimg, M, HW, C, false, st));
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, nullptr, st));
-  if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, nullptr, st, false))) return rc;
+  CKL(launch_rows_enter(x, static_cast<float*>(u.backup.p), fused ? nullptr : w.b_c, pimg, M, HW, C, w.attn, st));
+  // from here on x is only added to (L2 reductions): the grouped conv runs on the side stream, as in run_block
+  const bool fork = u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C);
+  if (fork) {
+    if (!u.side_stream) {
+      CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&u.ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(u.ev_fork, st));
+    CK(cudaStreamWaitEvent(u.side_stream, u.ev_fork, 0));
+    if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, nullptr, u.side_stream, false))) return rc;
+    CK(cudaEventRecord(u.ev_join, u.side_stream));
+  } else if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, nullptr, st, false))) return rc;
   const int ldh = 6 * C;                                   // hbuf row: [h_general | h_e0 .. h_e3 | attention]
   if (w.attn) {
     GemmDesc d = gd();
@@ -742,20 +757,29 @@ int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B,
          launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 5LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
                                  global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, nullptr, st));
   }
-  {
-    GemmDesc d = gd();                                     // all five experts: [M,C] . [C, 10C], ReGLU gate -> h [M, 5C]
+  if (fused) {
+    CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
+         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, nullptr, 0, 0, pimg, HW, st));
+    if (w.attn) {   // x += att . W_out^T + b_out for every image (skipped ones are restored below)
+      GemmDesc c = gd();
+      c.A = toff(h, u.hbuf.p, 5LL * C); c.lda = ldh; c.W = toff(h, w.w_c, 5LL * C * C); c.ldw = C; c.bias = w.b_c + 5LL * C;
+      c.out = x; c.ldo = C; c.M = M; c.N = C; c.K = C; c.epi = EPI_ACCUM_F32;
+      if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
+    }
+  } else {
+    GemmDesc d = gd();                                     // all five experts: [M,C] . [C, 10C], ReGLU gate (masked per image) -> h [M, 5C]
     d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
     d.M = M; d.N = 10 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
+    d.mask_plan = pimg; d.mask_rows = HW; d.mask_span = C;
     if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
-    CKL(launch_mask_experts(u.hbuf.p, ldh, h->bf16(), pimg, M, HW, C, st));
-    GemmDesc c = gd();                                     // x += [h | att] . [Wc_g | Wc_0..3 | W_out]^T, biases per image below
+    GemmDesc c = gd();                                     // x += [h | att] . [Wc_g | Wc_0..3 | W_out]^T (biases: rows_enter)
     c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = nullptr; c.out = x; c.ldo = C;
     c.M = M; c.N = C; c.K = (w.attn ? 6 : 5) * C; c.epi = EPI_ACCUM_F32;
     c.sel = 3; c.sel_span = C; c.sel_stride = C;
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
-    CKL(launch_rows_bias(x, w.b_c, pimg, M, HW, C, w.attn, st));
   }
-  CKL(launch_skip_rows(x, static_cast<float*>(u.backup.p), pimg, M, HW, C, true, st));
+  if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
+  CKL(launch_rows_leave(x, static_cast<const float*>(u.backup.p), pimg, M, HW, C, st));
   return LDMB_OK;
 }
 
@@ -1397,6 +1421,6 @@ extern "C" int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, 
   if (!h->bf16() || !mlp_fused_supported(M, C)) return fail(h, LDMB_ERR_UNSUPPORTED, "fused feed-forward: bf16 mode, C = 128 or 256");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, st));
+  CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, nullptr, 0, st));
   return LDMB_OK;
 }
