@@ -23,23 +23,29 @@ namespace {
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
-template <int C, int CG> struct MlpCfg {
+// RES (C = 128 pairs, one plan for the batch): the three experts' Wab / Wc tiles stay RESIDENT in shared memory for all
+// tiles of the CTA (loaded once, before the previous kernel has finished) instead of streaming through the rings per
+// tile -- at 4 tiles per CTA the re-streamed weights were 144 of the 176 KB a CTA ingests per tile.
+template <int C, int CG, bool RES> struct MlpCfg {
   static constexpr int NKB = C / 64;                       // k-blocks of GEMM1 = 64-column h chunks per expert
   static constexpr int UNITS = 3 * NKB;
   static constexpr int A1_BYTES = NKB * 128 * 128;         // xm tile: NKB k-block tiles of [128 rows x 128 B]
-  static constexpr int A1_BUFS = (C == 128 && CG == 2) ? 2 : 1;
+  static constexpr int A1_BUFS = (C == 128 && CG == 2 && !RES) ? 2 : 1;
   // One W1 stage = all NKB k-block tiles of a unit's Wab rows, one W2 stage = the unit's Wc tile: a unit costs the MMA
   // thread two tcgen05.commit (GEMM1 done, GEMM2 done) -- commits, not MMAs, bounded the first version of this kernel.
   static constexpr int B1_ROWS = 128 / CG, W1_BYTES = NKB * B1_ROWS * 128;
   static constexpr int B2_ROWS = C / CG, W2_BYTES = B2_ROWS * 128;
   static constexpr int ND1 = C == 128 ? 3 : 2;             // D1 accumulators (128 TMEM columns each)
   static constexpr int LAG = ND1 - 1;                      // GEMM2(u) is issued LAG units behind GEMM1: hides the MMA->epilogue->MMA round trip
-  static constexpr int W1S = C == 128 ? (CG == 2 ? 5 : 3) : 2;
-  static constexpr int HS = (C == 128 && CG == 2) ? 3 : 2;  // h slots == W2 stages (one barrier frees both)
+  static constexpr int W1S = RES ? UNITS : (C == 128 ? (CG == 2 ? 5 : 3) : 2);
+  static constexpr int HS = (C == 128 && CG == 2 && !RES) ? 3 : 2;  // h slots; streaming: == W2 stages (one barrier frees both)
+  static constexpr int W2S = RES ? UNITS : HS;
   static constexpr int H_BYTES = 128 * 128;
   static constexpr int D2_COL = ND1 * 128;
   static constexpr int SLAB_BYTES = 32 * 128;              // epilogue-2 staging aliases the (then idle) h ring
-  static constexpr int TILE_BYTES = A1_BUFS * A1_BYTES + W1S * W1_BYTES + HS * (W2_BYTES + H_BYTES);
+  static constexpr int TILE_BYTES = A1_BUFS * A1_BYTES + W1S * W1_BYTES + W2S * W2_BYTES + HS * H_BYTES;
+  static_assert(!RES || (C == 128 && CG == 2), "resident weights fit for C = 128 pairs only");
+  static_assert(W1S <= 8 && W2S <= 8, "barrier slots");
   static constexpr int BAR_BYTES = 512;
   static constexpr int BIAS_FLOATS = 5 * 2 * C + 2 * C;    // a|b biases of all five experts + the tile's summed c biases (x2)
   static constexpr int SMEM_BYTES = 1024 + TILE_BYTES + BAR_BYTES + BIAS_FLOATS * 4;
@@ -103,23 +109,23 @@ struct Ring {
   __device__ __forceinline__ void next(uint32_t n) { if (++i == n) { i = 0; ph ^= 1; } }
 };
 
-template <int C, int CG>
+template <int C, int CG, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWab,
                  const __grid_constant__ CUtensorMap tmWc, const __grid_constant__ CUtensorMap tmO, const MlpArgs a, int* fault, long long* trace) {
-  using Cfg = MlpCfg<C, CG>;
-  constexpr int NKB = Cfg::NKB, UNITS = Cfg::UNITS, LAG = Cfg::LAG, ND1 = Cfg::ND1, W1S = Cfg::W1S, HS = Cfg::HS;
+  using Cfg = MlpCfg<C, CG, RES>;
+  constexpr int NKB = Cfg::NKB, UNITS = Cfg::UNITS, LAG = Cfg::LAG, ND1 = Cfg::ND1, W1S = Cfg::W1S, HS = Cfg::HS, W2S = Cfg::W2S;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* a1 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w1 = a1 + Cfg::A1_BUFS * Cfg::A1_BYTES;
   uint8_t* w2 = w1 + W1S * Cfg::W1_BYTES;
-  uint8_t* hs = w2 + HS * Cfg::W2_BYTES;
+  uint8_t* hs = w2 + W2S * Cfg::W2_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(hs + HS * Cfg::H_BYTES);
   uint64_t* a1_full = bars;                       uint64_t* a1_empty = a1_full + 2;
   uint64_t* w1_full = a1_empty + 2;               uint64_t* g1_done = w1_full + 8;     // GEMM1(u) complete: D1 full AND W1 stage free
-  uint64_t* w2_full = g1_done + 8;                uint64_t* g2_done = w2_full + 4;     // GEMM2(u) complete: h slot AND W2 stage free
+  uint64_t* w2_full = g1_done + 8;                uint64_t* g2_done = w2_full + 8;     // GEMM2(u) complete: h slot AND W2 stage free
   uint64_t* h_full = g2_done + 4;                 uint64_t* d1_empty = h_full + 4;
   uint64_t* d2_full = d1_empty + 4;               uint64_t* d2_empty = d2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
@@ -132,7 +138,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A1_BUFS; ++i) { ptx::mbar_init(&a1_full[i], 1); ptx::mbar_init(&a1_empty[i], 1); }
     for (int i = 0; i < W1S; ++i) { ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&g1_done[i], 1); }
-    for (int i = 0; i < HS; ++i) { ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&g2_done[i], 1); ptx::mbar_init(&h_full[i], kEpiWarps * CG); }
+    for (int i = 0; i < W2S; ++i) ptx::mbar_init(&w2_full[i], 1);
+    for (int i = 0; i < HS; ++i) { ptx::mbar_init(&g2_done[i], 1); ptx::mbar_init(&h_full[i], kEpiWarps * CG); }
     for (int i = 0; i < ND1; ++i) ptx::mbar_init(&d1_empty[i], kEpiWarps * CG);
     ptx::mbar_init(d2_full, 1); ptx::mbar_init(d2_empty, kEpiWarps * CG);
     *s_abort = 0;
@@ -187,7 +194,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto slot_of = [&](int ti, int e) -> int { return e == 0 ? 0 : 1 + ((tile_word(ti) >> (8 * e)) & 0xff); };
       auto issue_w1 = [&]() {
         const int u = n1 % UNITS, e = u / NKB, j = u % NKB;
-        if (!wait_bar(&g1_done[r1.i], r1.ph ^ 1, s_abort, fault, 22)) { ok = false; return; }
+        if (!RES && !wait_bar(&g1_done[r1.i], r1.ph ^ 1, s_abort, fault, 22)) { ok = false; return; }
         if (leader) ptx::mbar_arrive_expect_tx(&w1_full[r1.i], Cfg::W1_BYTES * CG);
         const int row = slot_of(w1_ti, e) * 2 * C + j * 128 + (int)rank * Cfg::B1_ROWS;
         for (int kb = 0; kb < NKB; ++kb) {
@@ -200,17 +207,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       auto issue_w2 = [&]() {
         const int u = n2 % UNITS, e = u / NKB, j = u % NKB;
-        if (!wait_bar(&g2_done[r2.i], r2.ph ^ 1, s_abort, fault, 23)) { ok = false; return; }
+        if (!RES && !wait_bar(&g2_done[r2.i], r2.ph ^ 1, s_abort, fault, 23)) { ok = false; return; }
         if (leader) ptx::mbar_arrive_expect_tx(&w2_full[r2.i], Cfg::W2_BYTES * CG);
         const int row = slot_of(w2_ti, e) * C + (int)rank * Cfg::B2_ROWS;
         if (CG == 2) ptx::tma_load_2d_2sm(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
         else ptx::tma_load_2d(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
-        r2.next(HS);
+        r2.next(W2S);
         if (++n2 % UNITS == 0) w2_ti = next_active(w2_ti + 1);
       };
       // fill both weight rings while the previous kernel is still draining; only the xm tiles wait for it
       while (ok && w1_ti < my_tiles && n1 < W1S) issue_w1();
-      while (ok && w2_ti < my_tiles && n2 < HS) issue_w2();
+      while (ok && w2_ti < my_tiles && n2 < W2S) issue_w2();      // RES: W1S = W2S = UNITS -- every weight tile, once
       pdl_wait();
       trace_stamp(trace, 2);
       int ta = 0;                                           // ordinal of the tile among this CTA's active tiles
@@ -224,7 +231,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           else ptx::tma_load_2d(dst, &tmX, &a1_full[ra.i], kb * 64, m0);
         }
         ra.next(Cfg::A1_BUFS);
-        for (int s = 0; ok && s < UNITS + LAG; ++s) {     // same order as the MMA thread consumes
+        for (int s = 0; !RES && ok && s < UNITS + LAG; ++s) {     // same order as the MMA thread consumes
           if (s < UNITS && ta * UNITS + s >= n1) issue_w1();
           if (ok && s >= LAG && ta * UNITS + s - LAG >= n2) issue_w2();
         }
@@ -253,7 +260,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int s = 0; ok && s < UNITS + LAG; ++s) {
           if (s < UNITS) {
             if (!wait_bar(&d1_empty[rd1.i], rd1.ph ^ 1, s_abort, fault, 25)) { ok = false; break; }
-            if (!wait_bar(&w1_full[r1.i], r1.ph, s_abort, fault, 26)) { ok = false; break; }
+            if (!wait_bar(&w1_full[r1.i], RES ? 0u : r1.ph, s_abort, fault, 26)) { ok = false; break; }   // RES: landed once, stays
             ptx::tc_fence_after();
             const uint32_t d1 = tmem_base + rd1.i * 128;
             const uint32_t bb = ptx::smem_u32(w1 + r1.i * Cfg::W1_BYTES);
@@ -275,9 +282,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               if (!wait_bar(d2_empty, rd2.ph ^ 1, s_abort, fault, 27)) { ok = false; break; }
             }
             if (!wait_bar(&h_full[r2.i], r2.ph, s_abort, fault, 28)) { ok = false; break; }
-            if (!wait_bar(&w2_full[r2.i], r2.ph, s_abort, fault, 29)) { ok = false; break; }
+            const uint32_t w2i = RES ? (uint32_t)u : r2.i;
+            if (!wait_bar(&w2_full[w2i], RES ? 0u : r2.ph, s_abort, fault, 29)) { ok = false; break; }
             ptx::tc_fence_after();
-            const uint32_t ha = ptx::smem_u32(hs + r2.i * Cfg::H_BYTES), bb = ptx::smem_u32(w2 + r2.i * Cfg::W2_BYTES);
+            const uint32_t ha = ptx::smem_u32(hs + r2.i * Cfg::H_BYTES), bb = ptx::smem_u32(w2 + w2i * Cfg::W2_BYTES);
             if (!(a.dbg & 2)) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) mma(d2, ha + k * 32, bb + k * 32, idesc2, (u | k) != 0 ? 1u : 0u);
@@ -309,27 +317,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int ti = next_active(0); ok && ti < my_tiles; ++ta) {
       const int m0 = (t0 + ti * t_step) * (128 * CG) + (int)rank * 128;
       const int word = tile_word(ti);
-      const int slot_e[3] = {0, 1 + ((word >> 8) & 0xff), 1 + ((word >> 16) & 0xff)};   // row blocks of the stacked expert biases
       const int ti_next = next_active(ti + 1);
       if (ti_next < my_tiles && (int)threadIdx.x - 64 < C)      // the next tile's c biases: visible after this tile's closing barrier
         sb_c[((ta + 1) & 1) * C + threadIdx.x - 64] = c_bias_sum(tile_word(ti_next), threadIdx.x - 64);
       const float* sbc = sb_c + (ta & 1) * C;
       for (int u = 0; u < UNITS; ++u) {
-        const float* sb = sb_ab + slot_e[u / NKB] * 2 * C + (u % NKB) * 128;     // [64 a-biases | 64 b-biases] of this unit
+        const int e = u / NKB, slot = e == 0 ? 0 : 1 + ((word >> (8 * e)) & 0xff);   // row block of the stacked expert biases
+        const float* sb = sb_ab + slot * 2 * C + (u % NKB) * 128;                     // [64 a-biases | 64 b-biases] of this unit
         if (!wait_bar(&g1_done[re1.i], re1.ph, s_abort, fault, 30)) { ok = false; break; }
         if (threadIdx.x == 64 && ta == 0 && u == 0) trace_stamp(trace, 6);
         if (!wait_bar(&g2_done[rh.i], rh.ph ^ 1, s_abort, fault, 31)) { ok = false; break; }   // h slot free
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + lane_off + rd1.i * 128;
         if (!(a.dbg & 1)) {
+          const int ch = chalf;                                // 32-column half of the unit's 64 h columns
           uint32_t ra_[32], rb_[32];
-          ptx::tmem_ld_32x32(t_row + chalf * 32, ra_);
-          ptx::tmem_ld_32x32(t_row + 64 + chalf * 32, rb_);
+          ptx::tmem_ld_32x32(t_row + ch * 32, ra_);
+          ptx::tmem_ld_32x32(t_row + 64 + ch * 32, rb_);
           ptx::tmem_ld_wait();
           // gate: (a + bias_a) * relu(b + bias_b); biases as 16-byte shared loads, adds / multiply as packed f32x2
           float v[32];
-          const float4* sa4 = reinterpret_cast<const float4*>(sb + chalf * 32);
-          const float4* sb4 = reinterpret_cast<const float4*>(sb + 64 + chalf * 32);
+          const float4* sa4 = reinterpret_cast<const float4*>(sb + ch * 32);
+          const float4* sb4 = reinterpret_cast<const float4*>(sb + 64 + ch * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 ba = sa4[i], bb = sb4[i];
@@ -341,11 +350,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             a01 = mul2(a01, g01); a23 = mul2(a23, g23);
             v[4 * i] = a01.x; v[4 * i + 1] = a01.y; v[4 * i + 2] = a23.x; v[4 * i + 3] = a23.y;
           }
-          // row r = q*32 + lane of the [128 x 64] bf16 chunk, 16-byte pieces chalf*4 .. +4, 128B-swizzled (piece ^ (r & 7))
+          // row r = q*32 + lane of the [128 x 64] bf16 chunk, 16-byte pieces ch*4 .. +4, 128B-swizzled (piece ^ (r & 7))
           const uint32_t hrow = ptx::smem_u32(hs + rh.i * Cfg::H_BYTES) + (q * 32 + lane) * 128;
 #pragma unroll
           for (int p = 0; p < 4; ++p)
-            ptx::st_shared_v4(hrow + (((chalf * 4 + p) ^ sw) << 4), pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
+            ptx::st_shared_v4(hrow + (((ch * 4 + p) ^ sw) << 4), pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
                               pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
         }
         ptx::fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
@@ -403,13 +412,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (threadIdx.x == 0) trace_stamp(trace, 9);
 }
 
-template <int C, int CG>
+template <int C, int CG, bool RES>
 cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMap& tmWab, const CUtensorMap& tmWc, const CUtensorMap& tmO,
                         const MlpArgs& a, cudaStream_t st) {
-  using Cfg = MlpCfg<C, CG>;
+  using Cfg = MlpCfg<C, CG, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, CG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -422,7 +431,7 @@ cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMa
   if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   if (CG == 2) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
   cfg.attrs = at; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, mlp_fused_kernel<C, CG>, tmX, tmWab, tmWc, tmO, a, ctx->fault_dev, ctx->trace_dev);
+  return cudaLaunchKernelEx(&cfg, mlp_fused_kernel<C, CG, RES>, tmX, tmWab, tmWc, tmO, a, ctx->fault_dev, ctx->trace_dev);
 }
 
 }  // namespace
@@ -476,6 +485,8 @@ cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, c
   if (!enc(&tmWab, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_ab, C, 5 * 2 * C, 2, 64, 128 / cg)) return cudaErrorInvalidValue;
   if (!enc(&tmWc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_c, C, w_c_rows, 2, 64, C / cg)) return cudaErrorInvalidValue;
   if (!enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, C, M, 4, 32, 32)) return cudaErrorInvalidValue;
-  if (C == 128) return cg == 2 ? launch_inst<128, 2>(ctx, tmX, tmWab, tmWc, tmO, a, st) : launch_inst<128, 1>(ctx, tmX, tmWab, tmWc, tmO, a, st);
-  return launch_inst<256, 2>(ctx, tmX, tmWab, tmWc, tmO, a, st);
+  static const bool resident = getenv("LDMB_MLP_RES") == nullptr || atoi(getenv("LDMB_MLP_RES")) != 0;
+  if (C == 128 && cg == 2 && plan_img == nullptr && resident) return launch_inst<128, 2, true>(ctx, tmX, tmWab, tmWc, tmO, a, st);
+  if (C == 128) return cg == 2 ? launch_inst<128, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st) : launch_inst<128, 1, false>(ctx, tmX, tmWab, tmWc, tmO, a, st);
+  return launch_inst<256, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st);
 }
