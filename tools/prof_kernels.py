@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch single kernels of the config-2 workload eagerly through the C ABI (for `ncu --set full -k regex:...`).
-WHICH=gconv:2 | gemm_ab:3 | gemm_c:2 | norm:0 | attn:0 (kernel:level); each is launched REPS times."""
+WHICH=gconv:2 | gemm_ab:3 | gemm_c:2 | norm:0 | attn:0 | mlp:0 (kernel:level); each is launched REPS times."""
 import os
 import sys
 
@@ -34,6 +34,9 @@ for _ in range(reps):
     elif which == "norm":
         film = torch.randn(H * H, 2 * C, device="cuda", generator=g)
         h.channelnorm_film(x, film, xm, M, C, H * H)
+    elif which == "mlp":
+        w_ab = torch.randn(10 * C, C, device="cuda", generator=g).bfloat16(); w_c = torch.randn(5 * C, C, device="cuda", generator=g).bfloat16()
+        h.mlp_fused(xm, w_ab, torch.zeros(10 * C, device="cuda"), w_c, torch.zeros(5 * C, device="cuda"), x, M, C, 1, 2)
     elif which == "attn":
         qkv = torch.randn(B, H, H, 3 * C, device="cuda", generator=g).bfloat16()
         att = torch.empty(B, H, H, 4 * C, device="cuda", dtype=torch.bfloat16)
