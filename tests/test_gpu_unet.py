@@ -143,17 +143,20 @@ def test_full_size_step_vs_oracle_and_shard_equivalence():
     assert_no_fault(model)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_per_image_plans_match_batch1_forwards(precision):
+@pytest.mark.parametrize("precision,hw", [("fp32", (16, 16)), ("bf16", (16, 16)), ("bf16", (32, 32)), ("bf16", (8, 16)), ("bf16", (12, 20))])
+def test_per_image_plans_match_batch1_forwards(precision, hw):
     """A batch with PER-IMAGE stochastic-depth / expert decisions (what the reference's batch-1 sample loops compute,
     sample_ldm.py:71-72) against the oracle run image by image with that image's plan; real channel widths, attention
-    blocks, per-sample timesteps, train mode (skips).  Python's `random` is consumed in image order."""
+    blocks, per-sample timesteps, train mode (skips).  Python's `random` is consumed in image order.
+    Resolutions pick the paths: 16x16 = per-tile experts in the fused feed-forward at C = 128 (256 pixels: one CTA-pair
+    tile per image) + dense masked GEMMs at C = 256; 32x32 = fused at both widths; 8x16 = the single-CTA fused variant
+    (128 pixels per image); 12x20 = no whole tiles per image anywhere (dense at both widths)."""
     cfg = R.UNetCfg(input_channels=8, stages=(2, 2), channels=(128, 256))
     sd = R.make_unet_state(cfg, 31)
     model = build_unet(cfg, sd, precision)
     model.train(True)
     B = 5
-    x = torch.randn(B, 8, 16, 16); t = torch.tensor([10, 999, 10, 500, 3])
+    x = torch.randn(B, 8, *hw); t = torch.tensor([10, 999, 10, 500, 3])
     nblk = len(R.block_table(cfg))
     random.seed(77)
     with torch.no_grad():
@@ -165,6 +168,6 @@ def test_per_image_plans_match_batch1_forwards(precision):
     assert len({tuple(p) for p in plans}) > 1 and any(e[0] for p in plans for e in p)     # plans differ, some blocks skipped
     want = torch.cat([R.unet_forward(sd, cfg, x[b:b + 1], t[b:b + 1], plans[b]) for b in range(B)])
     err = R.rel_l2(y, want)
-    print(f"per-image plans {precision}: rel-L2 {err:.3e}")
+    print(f"per-image plans {precision} {hw}: rel-L2 {err:.3e}")
     assert err < (FP32_STEP_TOL if precision == "fp32" else BF16_STEP_TOL), err
     assert_no_fault(model)
