@@ -48,7 +48,7 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
 // encoder_first (unet.py:77,90): x NCHW fp32 [B,Cin,H*s,W*s] -> out fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]
 // x is read through sp->x_in (device-side step parameters)
 cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias, float* out,
-                        int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
+                        int B, int Cin, int H, int W, int s, int C0, bool tf32, cudaStream_t st);
 // ChannelNorm + FiLM (modules.py:23-25, unet.py:22): out(T)[m,c] = norm(x[m,:])[c]*film[row,c] + film[row,C+c]
 // film row = t_index[m / HW] * HW + m % HW  (t_index may be NULL -> 0)
 // skip (device, may be NULL): non-zero => the block is skipped this step and the kernel exits
@@ -74,7 +74,7 @@ cudaError_t launch_window_attention_mma(const void* qkv, const void* xm, const f
 // x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; x_in/out/noise NCHW fp32 [B,Cin,H*s,W*s]; ddim_enabled 0 = eps only.
 // sp (device): x_in / out / noise pointers and the DDIM scalars of this step.
 cudaError_t launch_final(const float* x, const float* w, const float* bias, const StepParams* sp,
-                         int B, int Cin, int H, int W, int s, int C0, cudaStream_t st);
+                         int B, int Cin, int H, int W, int s, int C0, bool tf32, cudaStream_t st);
 
 // ---- per-image plans (plan word per image: skip | e1 << 8 | e2 << 16; see kernels_simt.cu)
 cudaError_t launch_rows_enter(float* x, float* backup, const float* b_c, const int* plan_img, int M, int HW, int C, bool attn,

@@ -753,6 +753,122 @@ __global__ void __launch_bounds__(256) final_warp_kernel(const float* __restrict
   }
 }
 
+// -------------------------------------------------------------------------------------
+// TF32 tensor-core versions of the two edge layers for the bf16 mode (the fp32 validation mode keeps the exact kernels
+// above).  Both are skinny GEMMs -- stem [M x J<=8] . [J x C0], last layer [M x C0] . [C0 x J<=8] -- whose SIMT forms
+// are instruction-bound (190 / 225 warp instructions per pixel against 33.5 MB of fp32 traffic at config 2); as
+// mma.sync.m16n8k8 they cost 4 / 10 and run at the speed of the x tensor they write / read.
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// offset of input/output element j of pixel m in the NCHW fp32 tensor [B, Cin, H*s, W*s] (k = stride = s)
+__device__ __forceinline__ long long nchw_offset(int m, int j, int Cin, int H, int W, int s) {
+  const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
+  const int ci = j / (s * s), dy = (j / s) % s, dx = j % s;
+  return (((long long)b * Cin + ci) * (H * s) + hh * s + dy) * (W * s) + ww * s + dx;
+}
+
+// encoder_first (unet.py:90): out fp32 [M, C0 = 128*V] = x_in(NCHW) . W^T + bias.  A warp takes 16 pixels: the A fragment is
+// 4 scalar loads per lane (8 consecutive pixels of one input plane per 32-byte sector), the [C0 x 8] weights live in
+// registers as B fragments, every MMA yields an 8-channel slice that is stored as one full 32-byte sector per pixel.
+template <int V>
+__global__ void __launch_bounds__(256) stem_mma_kernel(const StepParams* __restrict__ sp, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       int B, int Cin, int H, int W, int s) {
+  pdl_wait();
+  constexpr int C0 = 128 * V, NT = C0 / 8;
+  const float* __restrict__ x = sp->x_in;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int J = Cin * s * s, M = B * H * W;
+  uint32_t wb[NT][2];
+  float bz[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    wb[nt][0] = to_tf32(t < J ? w[(nt * 8 + g) * J + t] : 0.f);            // B(k = t,     n = g)
+    wb[nt][1] = to_tf32(t + 4 < J ? w[(nt * 8 + g) * J + t + 4] : 0.f);    // B(k = t + 4, n = g)
+    bz[nt][0] = bias[nt * 8 + 2 * t]; bz[nt][1] = bias[nt * 8 + 2 * t + 1];
+  }
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16; mb < M; mb += wpg * 16) {
+    const int m0 = mb + g, m1 = mb + g + 8;
+    const uint32_t a0 = to_tf32(m0 < M && t < J ? x[nchw_offset(m0, t, Cin, H, W, s)] : 0.f);
+    const uint32_t a1 = to_tf32(m1 < M && t < J ? x[nchw_offset(m1, t, Cin, H, W, s)] : 0.f);
+    const uint32_t a2 = to_tf32(m0 < M && t + 4 < J ? x[nchw_offset(m0, t + 4, Cin, H, W, s)] : 0.f);
+    const uint32_t a3 = to_tf32(m1 < M && t + 4 < J ? x[nchw_offset(m1, t + 4, Cin, H, W, s)] : 0.f);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float c[4] = {bz[nt][0], bz[nt][1], bz[nt][0], bz[nt][1]};
+      mma_tf32(c, a0, a1, a2, a3, wb[nt][0], wb[nt][1]);
+      if (m0 < M) *reinterpret_cast<float2*>(out + (long long)m0 * C0 + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+      if (m1 < M) *reinterpret_cast<float2*>(out + (long long)m1 * C0 + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
+    }
+  }
+}
+
+// decoder_last (unet.py:102) + DDIM update (ddpm.py:81-91): eps[m, j] = x[m, :] . W[:, j] + bias.  A warp takes 16 pixels;
+// a lane loads 16-byte pieces of rows g and g + 8 and feeds them to the MMAs with the k index permuted (the dot product
+// does not care; the register-resident B fragments use the same permutation): piece (x, y, z, w) of 16-channel chunk kc =
+// channels 16 kc + 4 t + {0, 1, 2, 3} -> k-step 2 kc uses (x, y) as columns (t, t + 4), k-step 2 kc + 1 uses (z, w).
+template <int V>
+__global__ void __launch_bounds__(256) final_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const StepParams* __restrict__ sp,
+                                                        int B, int Cin, int H, int W, int s) {
+  pdl_wait();
+  constexpr int C0 = 128 * V, KC = C0 / 16;
+  const StepParams co = *sp;
+  const float* __restrict__ xin = co.x_in;
+  const float* __restrict__ noise = co.noise;
+  float* __restrict__ out = co.out;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int J = Cin * s * s, M = B * H * W;
+  uint32_t wb[KC][4];                                     // B(k, n = g) for the four channels of this lane's piece
+#pragma unroll
+  for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wb[kc][i] = to_tf32(g < J ? w[(kc * 16 + 4 * t + i) * J + g] : 0.f);
+  const int j0 = 2 * t, j1 = 2 * t + 1;                   // the outputs this lane owns after the MMAs (rows g and g + 8)
+  const float b0 = j0 < J ? bias[j0 / (s * s)] : 0.f, b1 = j1 < J ? bias[j1 / (s * s)] : 0.f;
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16; mb < M; mb += wpg * 16) {
+    const int m0 = mb + g, m1 = mb + g + 8;
+    float4 xa[KC], xb[KC];
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      xa[kc] = m0 < M ? __ldg(reinterpret_cast<const float4*>(x + (long long)m0 * C0 + kc * 16 + 4 * t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[kc] = m1 < M ? __ldg(reinterpret_cast<const float4*>(x + (long long)m1 * C0 + kc * 16 + 4 * t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float c[4] = {b0, b1, b0, b1};
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      mma_tf32(c, to_tf32(xa[kc].x), to_tf32(xb[kc].x), to_tf32(xa[kc].y), to_tf32(xb[kc].y), wb[kc][0], wb[kc][1]);
+      mma_tf32(c, to_tf32(xa[kc].z), to_tf32(xb[kc].z), to_tf32(xa[kc].w), to_tf32(xb[kc].w), wb[kc][2], wb[kc][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = i < 2 ? m0 : m1, j = (i & 1) ? j1 : j0;
+      if (m >= M || j >= J) continue;
+      const long long o = nchw_offset(m, j, Cin, H, W, s);
+      const float eps = c[i];
+      float r = eps;
+      if (co.ddim_enabled) {
+        const float x0 = (xin[o] - co.c_eps_in * eps) / co.c_div;
+        if (co.final_step) r = x0;
+        else {
+          r = co.c_x0 * x0 + co.c_eps_out * eps;
+          r += co.sigma * (noise ? noise[o] : 0.f);
+        }
+      }
+      out[o] = r;
+    }
+  }
+}
+
 // NHWC T [B,H,W,C] -> NCHW fp32 [B,Cout,H,W] 1x1 conv (+ bilinear x2 of prev [B,Cout,H/2,W/2], + uint8 HWC copy)
 template <typename T>
 __global__ void __launch_bounds__(256) pointwise_out_kernel(const T* __restrict__ x, const float* __restrict__ w,
@@ -943,9 +1059,15 @@ cudaError_t launch_repack(const float* src, void* dst, bool dst_bf16, const int 
 }
 
 cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
-                        int s, int C0, cudaStream_t st) {
+                        int s, int C0, bool tf32, cudaStream_t st) {
   const long long M = (long long)B * H * W;
   const int J = Cin * s * s;
+  if (tf32 && J <= 8 && (C0 == 128 || C0 == 256) && M < (1LL << 31)) {
+    const int grid = grid_for(M * 2, 256, 148 * 8);           // a warp per 16 pixels
+    if (C0 == 128) launch_k((stem_mma_kernel<1>), grid, 256, 0, st, sp, w, bias, out, B, Cin, H, W, s);
+    else launch_k((stem_mma_kernel<2>), grid, 256, 0, st, sp, w, bias, out, B, Cin, H, W, s);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)(kPixIn * (J + 1) + C0 * J) * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorNotSupported;
   launch_k((pointwise_in_kernel<float>), (unsigned)((M + kPixIn - 1) / kPixIn), 256, smem, st, nullptr, sp, w, bias, out, B, Cin, H, W, s, C0);
@@ -1062,9 +1184,15 @@ cudaError_t launch_window_attention(const void* qkv, const void* xm, const float
 }
 
 cudaError_t launch_final(const float* x, const float* w, const float* bias, const StepParams* sp, int B, int Cin, int H,
-                         int W, int s, int C0, cudaStream_t st) {
+                         int W, int s, int C0, bool tf32, cudaStream_t st) {
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
+  if (tf32 && Cin * s * s <= 8 && (C0 == 128 || C0 == 256) && M < (1LL << 31)) {
+    const int grid = grid_for(M * 2, 256, 148 * 8);           // a warp per 16 pixels
+    if (C0 == 128) launch_k((final_mma_kernel<1>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s);
+    else launch_k((final_mma_kernel<2>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s);
+    return cudaGetLastError();
+  }
   if (Cin * s * s <= 8 && (C0 == 128 || C0 == 256)) {
     const int grid = grid_for(M * 8, 256, 148 * 8);
     if (C0 == 128) launch_k((final_warp_kernel<1>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s, C0);

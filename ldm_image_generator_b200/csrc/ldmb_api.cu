@@ -813,7 +813,7 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
       if ((rc = issue_encodings(h, l, (Hs >> l) * (Ws >> l), n_t, te_dev[l], st))) return rc;
   // ---- encoder_first (unet.py:90)
   CKLP(PK_EDGE, 0, launch_stem(u.sp_dev, u.w_first, u.b_first, static_cast<float*>(u.levels[0].xs.p), B, cfg.input_channels, Hs, Ws, s,
-                  cfg.channels[0], st));
+                  cfg.channels[0], h->bf16() && !h->force_simt, st));
   // ---- encoder (unet.py:92-98)
   int bi = 0;
   for (int l = 0; l < S; ++l) {
@@ -851,7 +851,7 @@ int issue_forward(ldmb_handle* h, int B, int Hs, int Ws, int n_t, const float* c
   }
   // ---- decoder_last (unet.py:102) + DDIM update (ddpm.py:81-91)
   CKLP(PK_EDGE, 0, launch_final(static_cast<const float*>(u.levels[0].xs.p), u.w_last, u.b_last, u.sp_dev, B, cfg.input_channels, Hs, Ws, s,
-                   cfg.channels[0], st));
+                   cfg.channels[0], h->bf16() && !h->force_simt, st));
   return LDMB_OK;
 }
 

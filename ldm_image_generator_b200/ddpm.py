@@ -121,6 +121,12 @@ class DDPM(nn.Module):
         bar = tqdm(total=len(pairs), disable=not progress)
         first = True
         chunk = self.model.film_chunk(x.shape[2] // self.model.stem_size, x.shape[3] // self.model.stem_size) if fused else 0
+        # ddpm.py:80 draws the noise every step, even for eta = 0 where it is multiplied by zero: the generator must end
+        # where the reference leaves it (un-reseeded multi-image loops), but nothing else consumes it inside the loop, so
+        # for eta = 0 the draws are consumed up front -- one real draw, then the Philox offset is advanced
+        draw_noise = not (fused and eta == 0)
+        if not draw_noise:
+            _skip_randn(x_shape, device, len(pairs))
         for i, (t, t_next) in enumerate(pairs):
             t, t_next = int(t), int(t_next)
             if fused and i % chunk == 0:
@@ -128,9 +134,7 @@ class DDPM(nn.Module):
                 self.model.precompute_film(x, [int(p[0]) for p in pairs[i:i + chunk]])
             co, sigma = self.ddim_scalars(alpha_cum, t, t_next, eta)
             if fused:
-                # ddpm.py:78 then :80 -- the noise is drawn every step (even for eta=0) so the torch
-                # generator stays in lock-step with the reference across un-reseeded calls
-                e = torch.randn(*x_shape, device=device)
+                e = torch.randn(*x_shape, device=device) if draw_noise else None     # ddpm.py:78 then :80
                 x = self.model.denoise_step(x, t, co, e if co.sigma != 0.0 else None, check_params=first)
                 first = False
             else:

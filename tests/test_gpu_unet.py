@@ -71,6 +71,29 @@ def test_unet_real_widths_nonsquare_batch_vs_oracle():
         assert_no_fault(model)
 
 
+@pytest.mark.parametrize("kw,shape", [
+    (dict(input_channels=3, stages=(1, 1), channels=(128, 256)), (3, 3, 10, 14)),                # config-1 style RGB input: J = 3
+    (dict(input_channels=2, stages=(1, 1), channels=(128, 256), stem_size=2), (3, 2, 20, 28)),   # patchify stem: J = 2*2*2
+    (dict(input_channels=8, stages=(1, 1), channels=(256, 512)), (2, 8, 12, 12)),                # first level of the wide UNet
+])
+def test_edge_layers_tensor_core_paths_vs_oracle(kw, shape):
+    """encoder_first / decoder_last (unet.py:90,102) run as TF32 mma.sync kernels in bf16 mode (exact SIMT kernels in
+    fp32 mode): fewer than 8 inputs per pixel (zero-padded k), a stem with stride, 256 channels, pixel counts that are
+    not a multiple of the 16-pixel MMA tile.  The step output goes through both layers."""
+    cfg = R.UNetCfg(**kw)
+    sd = R.make_unet_state(cfg, 77)
+    x = torch.randn(*shape); t = torch.tensor([500, 3, 999][:shape[0]])
+    random.seed(2)
+    plan = R.draw_plan(len(R.block_table(cfg)), False)
+    want = R.unet_forward(sd, cfg, x, t, plan)
+    for precision, tol in (("fp32", FP32_STEP_TOL), ("bf16", BF16_STEP_TOL)):
+        model = build_unet(cfg, sd, precision)
+        err = R.rel_l2(_run(model, x, t, plan), want)
+        print(f"edge layers {kw.get('input_channels')}ch stem {kw.get('stem_size', 1)} {precision}: {err:.3e}")
+        assert err < tol
+        assert_no_fault(model)
+
+
 def test_bad_inputs_raise_like_the_reference():
     cfg = R.UNetCfg(input_channels=8, stages=(1, 1), channels=(32, 64))
     model = build_unet(cfg, R.make_unet_state(cfg, 1), "fp32")
