@@ -38,6 +38,8 @@ struct TcTiling {
   int TW, TH, TB;   // AM_CONV3: the 128-pixel tile is TB images x TH rows x TW columns
   int tma_out;      // epilogue goes through smem + TMA store / reduce
   int max_stages;       // debug (LDMB_TC_STAGES): use only this many of the smem pipeline stages
+  int dbg;              // debug (LDMB_TC_DBG): 1 = the epilogue drains nothing (accumulators are released unread), 2 = no MMAs,
+                        // 4 = staged epilogue without its TMA stores / reduces, 8 = no per-tile bias staging + CTA barrier
   int splits, kb_per;   // split-K (EPI_ACCUM_F32 through TMA reduce-add only): tile t covers k-blocks [sp*kb_per, ...)
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
 };
@@ -242,6 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (tl.dbg & 2) break;
             if (CG == 2) ptx::umma_f16_2sm(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
                                            (kb != kb0 || k != 0) ? 1u : 0u);
             else ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
@@ -275,6 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
+      if (!(tl.dbg & 8) || t == (int)(blockIdx.x / CG))
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
         float bv = 0.f;
@@ -286,14 +290,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         sb[c] = bv;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (!(tl.dbg & 8) || t == (int)(blockIdx.x / CG)) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
       if (threadIdx.x == 64) trace_stamp(trace, t == (int)(blockIdx.x / CG) ? 6 : 7);   // first / latest accumulator ready
       ptx::tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < d.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if (tl.tma_out) {
+      if (tl.dbg & 1) {
+      } else if (tl.tma_out) {
         // ---- smem-staged epilogue: each warp owns rows [q*32, q*32+32) of the tile and its own two 4 KB slabs
         const int orow = m0 + q * 32 + z * tl.out_row_b;
         const int ocol_z = z * tl.out_col_b;
@@ -313,33 +318,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float v[32];
               if (d.epi == EPI_REGLU) {
                 uint32_t rb[32];
+                if (tl.dbg & 16) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) { r[i] = 0u; rb[i] = 0u; }
+                } else {
                 ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
                 ptx::tmem_ld_32x32(t_row + a0 + 64 + half * 32, rb);
                 ptx::tmem_ld_wait();
+                }
                 // per-image expert decisions: the 64-column slab lies inside one expert's block
                 const bool keep = d.mask_plan == nullptr || expert_kept(d, m, (n0 + a0) >> 1);
+                // biases as 16-byte shared loads (through a generic pointer they were 64 scalar loads per half)
+                const uint32_t sba = ptx::smem_u32(sb + a0 + half * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  v[i] = keep ? (__uint_as_float(r[i]) + sb[a0 + half * 32 + i]) *
-                                    fmaxf(__uint_as_float(rb[i]) + sb[a0 + 64 + half * 32 + i], 0.f)
-                              : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                  const float4 ba = ptx::ld_shared_v4(sba + i * 16), bg = ptx::ld_shared_v4(sba + 256 + i * 16);
+                  v[4 * i] = (__uint_as_float(r[4 * i]) + ba.x) * fmaxf(__uint_as_float(rb[4 * i]) + bg.x, 0.f);
+                  v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + ba.y) * fmaxf(__uint_as_float(rb[4 * i + 1]) + bg.y, 0.f);
+                  v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + ba.z) * fmaxf(__uint_as_float(rb[4 * i + 2]) + bg.z, 0.f);
+                  v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + ba.w) * fmaxf(__uint_as_float(rb[4 * i + 3]) + bg.w, 0.f);
+                }
+                if (!keep) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
               } else {
+                if (tl.dbg & 16) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) r[i] = 0u;
+                } else {
                 ptx::tmem_ld_32x32(t_row + a0 + half * 32, r);
                 ptx::tmem_ld_wait();
+                }
+                const uint32_t sba = ptx::smem_u32(sb + a0 + half * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { const float t = __uint_as_float(r[i]) + sb[a0 + half * 32 + i]; v[i] = fmaxf(t, 0.f) + ns * fminf(t, 0.f); }
+                for (int i = 0; i < 8; ++i) {
+                  const float4 ba = ptx::ld_shared_v4(sba + i * 16);
+                  const float t0 = __uint_as_float(r[4 * i]) + ba.x, t1 = __uint_as_float(r[4 * i + 1]) + ba.y;
+                  const float t2 = __uint_as_float(r[4 * i + 2]) + ba.z, t3 = __uint_as_float(r[4 * i + 3]) + ba.w;
+                  v[4 * i] = fmaxf(t0, 0.f) + ns * fminf(t0, 0.f); v[4 * i + 1] = fmaxf(t1, 0.f) + ns * fminf(t1, 0.f);
+                  v[4 * i + 2] = fmaxf(t2, 0.f) + ns * fminf(t2, 0.f); v[4 * i + 3] = fmaxf(t3, 0.f) + ns * fminf(t3, 0.f);
+                }
               }
+              if (!(tl.dbg & 32))
 #pragma unroll
               for (int u = 0; u < 4; ++u)
                 ptx::st_shared_v4(srow + (((half * 4 + u) ^ sw) << 4), pack_bf16(v[8 * u], v[8 * u + 1]),
                                   pack_bf16(v[8 * u + 2], v[8 * u + 3]), pack_bf16(v[8 * u + 4], v[8 * u + 5]),
                                   pack_bf16(v[8 * u + 6], v[8 * u + 7]));
             }
-            ptx::fence_proxy_async();
+            if (!(tl.dbg & 64)) ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
               const int ocol = (d.epi == EPI_REGLU ? ((n0 + a0) >> 1) : (n0 + a0)) + ocol_z;
-              ptx::tma_store_2d(&tmO, slab, ocol, orow);
+              if (!(tl.dbg & 4)) ptx::tma_store_2d(&tmO, slab, ocol, orow);
               ptx::bulk_commit();
             }
             slab_sel ^= 1;
@@ -356,8 +388,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tmem_ld_32x32(t_row + a0, r);
             ptx::tmem_ld_wait();
             float v[32];
+            {
+              const uint32_t sba = ptx::smem_u32(sb + a0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[a0 + i];
+              for (int i = 0; i < 8; ++i) {
+                const float4 ba = ptx::ld_shared_v4(sba + i * 16);
+                v[4 * i] = __uint_as_float(r[4 * i]) + ba.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + ba.y;
+                v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + ba.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + ba.w;
+              }
+            }
             if (d.epi == EPI_STORE_F32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f) + ns * fminf(v[i], 0.f);
@@ -369,7 +408,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (d.epi == EPI_ACCUM_F32) ptx::tma_reduce_add_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
+              if (tl.dbg & 4) {}
+              else if (d.epi == EPI_ACCUM_F32) ptx::tma_reduce_add_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
               else ptx::tma_store_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
               ptx::bulk_commit();
             }
@@ -696,6 +736,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   tl.total = tl.m_tiles * tl.n_tiles * batch;
   tl.splits = 1; tl.kb_per = tl.num_kb;
   tl.max_stages = getenv("LDMB_TC_STAGES") ? atoi(getenv("LDMB_TC_STAGES")) : 0;
+  tl.dbg = getenv("LDMB_TC_DBG") ? atoi(getenv("LDMB_TC_DBG")) : 0;
   tl.TW = tl.TH = tl.TB = 0;
 
   CUtensorMap tmA, tmB;

@@ -76,6 +76,11 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {   // <= N gr
 template <int N> __device__ __forceinline__ void bulk_wait() {        // <= N groups not yet complete
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
