@@ -256,6 +256,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "peak_source": pk["source"] + (", sustained (kernel timed inside a long step)" if tensor else ""),
                 "avg_launch_us": round(1000.0 * kernels[dom]["ms"] / kernels[dom]["launches"], 2)}
 
+    # The per-launch events above serialise the launches (no programmatic-dependent-launch overlap) and include each
+    # launch's latency.  What the dominant class costs INSIDE the graph-replayed step: the timed step with the class's
+    # launches dropped (ldmb_debug_skip_classes: results are garbage, the launch sequence and timing are not), subtracted.
+    if dom in unet._handle.PROFILE_CLASSES and not dom.startswith("vae"):
+        t_full, _ = timed(step_device, 2, 1)
+        unet._handle.skip_classes([dom])
+        t_skip, _ = timed(step_device, 2, 2)
+        unet._handle.skip_classes([])
+        timed(step_device, 0, 1)
+        marginal_ms = (t_full - t_skip) / 2
+        if marginal_ms > 0:
+            ach = classes[dom]["work"] / (marginal_ms * 1e-3) / (1e12 if tensor else 1e9)
+            roofline["in_step"] = {"class_ms_per_step": round(marginal_ms, 3), "achieved": round(ach, 2),
+                                   "frac": round(ach / peak, 4),
+                                   "note": "step time minus the step time with this class's launches dropped (graph replay, "
+                                           "PDL overlap and warm L2 as in the timed region)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
