@@ -34,6 +34,24 @@ if "wide" in which:
           f"({214.82 * B / (ms / steps):7.1f} TFLOP/s on the hoisted algorithmic 214.82 GFLOP per image-step), latent std {float(z.std()):.3f}")
     del unet, ddpm
     torch.cuda.empty_cache()
+if "full3" in which:
+    # configs[3] as stated: 1000-step DDPM schedule (num_steps = num_timesteps), 16 images per GPU, then decode to 512x512
+    B = int(os.environ.get("B", "16"))
+    unet, dec = UNet(channels=[256, 512, 1024, 2048]).cuda().eval(), Decoder().cuda().eval()
+    ddpm = DDPM(model=unet)
+    x = torch.randn(B, 8, 64, 64, device="cuda")
+
+    def run_full():
+        z = ddpm.sample((B, 8, 64, 64), seed=0, num_steps=1000, x_T=x, progress=False)
+        return dec.decode_to_uint8(z)
+    ms, img = timed(run_full, 1)
+    assert tuple(img.shape) == (B, 512, 512, 3) and unet._handle.device_fault() == 0 and dec._handle.device_fault() == 0
+    assert 0 < float(img.float().std())
+    print(f"configs[3] wide UNet, {B} images/GPU, 1000 DDIM steps + decode to 512x512: {ms / 1e3:7.2f} s per batch -> "
+          f"{B / ms * 1e3:6.2f} images/s per GPU (x8 GPUs, no collective on the path: {8 * B / ms * 1e3:6.1f} images/s), "
+          f"{(214.82 * 1000 + 322.34) * B / ms:7.1f} TFLOP/s")
+    del unet, ddpm, dec
+    torch.cuda.empty_cache()
 if "vae" in which:
     Bv = int(os.environ.get("BV", "16"))
     enc, dec = Encoder().cuda().eval(), Decoder().cuda().eval()
