@@ -38,8 +38,8 @@ def short(n):
     return n.replace("__nv_bfloat16", "bf16")[:44]
 
 
-# one step = from a stem kernel (pointwise_in_kernel<float>) ... take the last full step
-first = [i for i, e in enumerate(ev) if "pointwise_in_kernel<float" in e.name]      # the stem opens every step
+# one step = from a stem kernel (stem_mma_kernel; pointwise_in_kernel<float> in fp32 mode) ... take the last full step
+first = [i for i, e in enumerate(ev) if "stem_mma_kernel" in e.name or "pointwise_in_kernel<float" in e.name]      # the stem opens every step
 lo, hi = first[-2], first[-1]
 step = ev[lo:hi]
 t0 = step[0].time_range.start
