@@ -145,10 +145,23 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tap = 0; tap < ((g.dbg & 2) ? 1 : 9); ++tap) {
           const uint32_t a_addr = a_base + ((g.dbg & 4) ? (tap / 3) * 8 : ((tap / 3) * g.pitch + tap % 3)) * 128;   // dbg 4: 8-row aligned offsets (wrong results)
           const uint32_t w_addr = w_base + tap * kWTile;
+          if (g.dense || (g.dbg & 8)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + k * 32), idesc,
-                          (tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + k * 32), idesc,
+                            (tap | k) != 0 ? 1u : 0u);
+          } else {
+            // grouped: the slice's [64 out x 64 in] tap matrix is block-diagonal (two groups of 32 channels), so k-steps
+            // 0-1 (inputs of group 0) only feed output columns 0..31 and k-steps 2-3 columns 32..63: N = 32 MMAs on
+            // the matching 32 weight rows fetch half the B operand (the MMA is bound by its shared-memory operand reads)
+            constexpr uint32_t idesc32 = ptx::idesc_bf16(128, 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t grp = k >> 1;
+              ptx::umma_f16(d_tmem + grp * 32, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + grp * 32 * 128 + k * 32),
+                            idesc32, (tap | (k & 1)) != 0 ? 1u : 0u);
+            }
+          }
         }
         ptx::umma_commit(&empty[stage]);
         ptx::umma_commit(&tfull[as]);

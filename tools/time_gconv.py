@@ -1,0 +1,14 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+import torch
+from ldm_image_generator_b200 import runtime
+from tools.bench_kernels import timeit
+h = runtime.Handle(torch.device("cuda", 0), "bf16")
+for lvl in range(4):
+    B, C, H = 64, 128 << lvl, 32 >> lvl
+    xm = [torch.randn(B, H, H, C, device="cuda").bfloat16() for _ in range(3)]
+    x = [torch.randn(B, H, H, C, device="cuda") for _ in range(3)]
+    w = torch.randn(C, 576, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda")
+    us = timeit(lambda i: h.grouped_conv3x3(xm[i % 3], w, b, x[i % 3], B, H, H, C))
+    print(f"gconv level {lvl} (C={C}, {H}x{H}): {us:6.1f} us")
+assert h.device_fault() == 0
