@@ -410,6 +410,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) {
               if (tl.dbg & 4) {}
               else if (d.epi == EPI_ACCUM_F32) ptx::tma_reduce_add_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
+              else if (d.epi == EPI_UPADD) {
+                // nearest x2 up-sampling (unet.py:85): the slab's 32 low-resolution pixels (a ww x bh rectangle) are added to
+                // their four (dy, dx) positions of x viewed as [bh][dy][ww][dx][C] -- four bulk reduce-adds, one smem source
+                const int ms = m0 + q * 32;
+                const int ww0 = d.ctW >= 32 ? ms % d.ctW : 0, bh0 = ms / d.ctW;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) ptx::tma_reduce_add_5d(&tmO, slab, n0 + a0, q4 & 1, ww0, q4 >> 1, bh0);
+              }
               else ptx::tma_store_2d(&tmO, slab, n0 + a0 + ocol_z, orow);
               ptx::bulk_commit();
             }
@@ -721,13 +729,17 @@ static int g_tc_force_cg = getenv("LDMB_TC_CG") ? atoi(getenv("LDMB_TC_CG")) : 0
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   if (!tc_supported(d)) return cudaErrorNotSupported;
-  const int bn = pick_bn(d, ctx->num_sms);
+  int bn = pick_bn(d, ctx->num_sms);
   const int batch = d.batch > 0 ? d.batch : 1;
+  // the up-sampling ch_conv (EPI_UPADD: M = low-resolution pixels, 1024..16384 rows) has few output tiles: narrower
+  // tiles, single CTAs and split-K (below) put it on ~128 SMs instead of 16..32
+  if (d.epi == EPI_UPADD && bn == 256 && d.N % 128 == 0) bn = 128;
   // CTA pairs (cta_group::2) whenever there are at least two 128-row tiles to pair up
   int cg = d.M > BM ? 2 : 1;
   // residual GEMMs with few output tiles (deep UNet levels) are cut along K below: single-CTA tiles give twice the
   // CTAs per split and measured 7 % faster than pairs there (tools/time_cgemm.py)
-  if (d.epi == EPI_ACCUM_F32 && d.res == nullptr && (long long)((d.M + BM - 1) / BM) * ((d.N + bn - 1) / bn) * batch <= ctx->num_sms) cg = 1;
+  if (((d.epi == EPI_ACCUM_F32 && d.res == nullptr) || d.epi == EPI_UPADD) &&
+      (long long)((d.M + BM - 1) / BM) * ((d.N + bn - 1) / bn) * batch <= ctx->num_sms) cg = 1;
   if (g_tc_force_cg == 1 || g_tc_force_cg == 2) cg = g_tc_force_cg;
   TcTiling tl;
   tl.m_tiles = (d.M + BM * cg - 1) / (BM * cg);
@@ -783,8 +795,10 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   memset(&tmO, 0, sizeof(tmO));
   tl.tma_out = 0; tl.out_col_b = 0; tl.out_row_b = 0;
   {
-    const bool f32 = d.epi == EPI_STORE_F32 || d.epi == EPI_ACCUM_F32;
-    const bool mode_ok = (d.epi == EPI_STORE || d.epi == EPI_REGLU || f32) && d.res == nullptr;   // (EPI_UPADD scatters: direct path)
+    // EPI_UPADD: staged when a 32-row slab of low-resolution pixels is a rectangle of the image grid (else: red.v4 scatter)
+    const bool up = d.epi == EPI_UPADD && batch == 1 && d.ctW > 0 && (d.ctW % 32 == 0 || 32 % d.ctW == 0) && d.M % d.ctW == 0;
+    const bool f32 = d.epi == EPI_STORE_F32 || d.epi == EPI_ACCUM_F32 || up;
+    const bool mode_ok = (d.epi == EPI_STORE || d.epi == EPI_REGLU || f32) && d.res == nullptr;
     const int esz = f32 ? 4 : 2;
     const int slab_cols = f32 ? 32 : 64;
     const int out_n = d.epi == EPI_REGLU ? d.N / 2 : d.N;
@@ -795,7 +809,18 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
       else if (d.out_off_b % d.ldo == 0 && d.M % (BM * cg) == 0) {   /* no tile may spill into the next batch's rows */ tl.out_row_b = (int)(d.out_off_b / d.ldo); rows = (long long)tl.out_row_b * (batch - 1) + d.M; }
       else ok = false;
     }
-    if (ok) {
+    if (ok && up) {
+      const cuuint64_t W = (cuuint64_t)d.ctW, BH = (cuuint64_t)(d.M / d.ctW), ld = (cuuint64_t)d.ldo * 4;
+      const cuuint64_t gdim[5] = {(cuuint64_t)d.ldo, 2, W, 2, BH};
+      const cuuint64_t gstr[4] = {ld, 2 * ld, 2 * W * ld, 4 * W * ld};
+      const cuuint32_t wb = d.ctW >= 32 ? 32u : (cuuint32_t)d.ctW;
+      const cuuint32_t box[5] = {32, 1, wb, 1, 32 / wb};
+      const cuuint32_t ones5[5] = {1, 1, 1, 1, 1};
+      r = ctx->encode(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, d.out, gdim, gstr, box, ones5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+      tl.tma_out = 1;
+    } else if (ok) {
       const cuuint64_t gdim[2] = {(cuuint64_t)d.ldo, (cuuint64_t)rows};
       const cuuint64_t gstr[1] = {(cuuint64_t)d.ldo * esz};
       const cuuint32_t box[2] = {(cuuint32_t)slab_cols, 32};
@@ -808,7 +833,8 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   }
   // split-K: an accumulate-into-the-residual GEMM with too few output tiles to fill the machine (deep UNet levels:
   // M = 1024..4096 rows, K = 3C..4C) is cut along K; every slice reduce-adds its partial tile into x with TMA.
-  if (tl.tma_out && d.epi == EPI_ACCUM_F32 && g_tc_splitk && ctx->splitk) {
+  // (EPI_UPADD scatters its partial tiles with red.global.add: just as linear)
+  if (((tl.tma_out && d.epi == EPI_ACCUM_F32) || d.epi == EPI_UPADD) && g_tc_splitk && ctx->splitk) {
     const int base = tl.total * cg;
     int sp = ctx->num_sms / (base > 0 ? base : 1);
     if (sp > tl.num_kb / 4) sp = tl.num_kb / 4;              // at least 4 k-blocks (K = 256) per slice
