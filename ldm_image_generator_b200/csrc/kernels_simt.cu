@@ -1063,7 +1063,8 @@ cudaError_t launch_stem(const StepParams* sp, const float* w, const float* bias,
   const long long M = (long long)B * H * W;
   const int J = Cin * s * s;
   if (tf32 && J <= 8 && (C0 == 128 || C0 == 256) && M < (1LL << 31)) {
-    const int grid = grid_for(M * 2, 256, 148 * 8);           // a warp per 16 pixels
+    // a warp per 16 pixels, at most one resident wave of CTAs (122 / 220 registers per thread): the warps loop instead
+    const int grid = grid_for(M * 2, 256, C0 == 128 ? 148 * 2 : 148);
     if (C0 == 128) launch_k((stem_mma_kernel<1>), grid, 256, 0, st, sp, w, bias, out, B, Cin, H, W, s);
     else launch_k((stem_mma_kernel<2>), grid, 256, 0, st, sp, w, bias, out, B, Cin, H, W, s);
     return cudaGetLastError();
@@ -1188,7 +1189,7 @@ cudaError_t launch_final(const float* x, const float* w, const float* bias, cons
   if (Cin * s * s > 32) return cudaErrorNotSupported;
   const long long M = (long long)B * H * W;
   if (tf32 && Cin * s * s <= 8 && (C0 == 128 || C0 == 256) && M < (1LL << 31)) {
-    const int grid = grid_for(M * 2, 256, 148 * 8);           // a warp per 16 pixels
+    const int grid = grid_for(M * 2, 256, 148 * 2);           // a warp per 16 pixels, one resident wave (measured: 296 CTAs best)
     if (C0 == 128) launch_k((final_mma_kernel<1>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s);
     else launch_k((final_mma_kernel<2>), grid, 256, 0, st, x, w, bias, sp, B, Cin, H, W, s);
     return cudaGetLastError();
