@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
   const float scale_l2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
 #pragma unroll 1
   for (int mt = 0; mt < MT; ++mt) {
+    // a tile whose 16 query slots are all padding (windows on the padded border, tile padding): its outputs would be
+    // cropped (attention.py:56) -- nothing to compute.  Same decision in every warp of the CTA.
+    if (!__any_sync(0xffffffffu, lane < 16 && rowm[mt * 16 + (lane & 15)] >= 0)) continue;
     // ---- S = q k^T
     uint32_t qa[2][4];
 #pragma unroll
