@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
   __shared__ __align__(16) bf16 Vs[LP * kLd];
   __shared__ float kb[LP];
   __shared__ long long rowm[LP];
+  __shared__ __align__(16) bf16 padkv[2][kRow];   // k / v row of a pad token (x = 0 -> in_proj bias), this head chunk
   __shared__ __align__(8) uint64_t gbar;
   const int L = wh * ww;
   const int nww = Wp / ww, nwin = (Hp / wh) * nww;
@@ -100,6 +101,8 @@ __global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
     rowm[tid] = rm;
     kb[tid] = bias;
   }
+  for (int i = tid; i < 2 * kRow; i += 32 * kHC)            // once per CTA (the per-piece conversion in the fill loop below
+    padkv[i / kRow][i % kRow] = __float2bfloat16_rn(b_in[(1 + i / kRow) * C + ch0 + i % kRow]);   // was 42 % of the stall samples at level 2)
   __syncthreads();
   // ---- gather q | k | v rows of this (window, head chunk): one 256-byte bulk async copy (TMA, 1-d) per (token, matrix)
   //      issued by one thread each and tracked by an mbarrier -- a handful of instructions instead of a 14-iteration
@@ -115,16 +118,10 @@ __global__ void __launch_bounds__(32 * kHC) window_attention_mma_kernel(
         ptx_bulk_g2s(dst, qkv + m * 3 * C + (long long)which * C + ch0, kRow * 2, &gbar);
       } else {
         const bool bias_fill = m == -1 && which != 0;         // pad token: x = 0 -> k, v = in_proj bias (attention.py:19-23)
-        const float* bp = b_in + which * C + ch0;
-#pragma unroll 1
-        for (int piece = 0; piece < kRow / 8; ++piece) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (bias_fill) {
-            const float* b8 = bp + piece * 8;
-            v.x = pack2(b8[0], b8[1]); v.y = pack2(b8[2], b8[3]); v.z = pack2(b8[4], b8[5]); v.w = pack2(b8[6], b8[7]);
-          }
-          *reinterpret_cast<uint4*>(dst + piece * 8) = v;
-        }
+        const uint4* src = reinterpret_cast<const uint4*>(padkv[which == 2 ? 1 : 0]);
+#pragma unroll
+        for (int piece = 0; piece < kRow / 8; ++piece)
+          *reinterpret_cast<uint4*>(dst + piece * 8) = bias_fill ? src[piece] : make_uint4(0u, 0u, 0u, 0u);
       }
     }
     while (!ptx_mbar_try_wait(&gbar, 0)) {}
