@@ -138,28 +138,31 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (!wait_bar(&full[stage], phase, s_abort, fault, 14)) break;
         if (sp == sp0) trace_stamp(trace, 4);
         ptx::tc_fence_after();
-        const uint32_t a_base = ptx::smem_u32(stages + stage * g.stage_bytes);
-        const uint32_t w_base = ptx::smem_u32(wts);
+        // The MMA thread is issue-bound (ncu: ~21 SASS instructions per tcgen05.mma, most of them building the two
+        // shared-memory descriptors and moving them to uniform registers): the descriptors of a tile differ only in their
+        // 14-bit start-address field, so build one per tile / per kernel and ADD the (tap, k) offsets in 16-byte units.
+        const uint64_t a_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(stages + stage * g.stage_bytes));
+        const uint64_t w_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(wts));
         const uint32_t d_tmem = tmem_base + as * kSlice;
-#pragma unroll 1
-        for (int tap = 0; tap < ((g.dbg & 2) ? 1 : 9); ++tap) {
-          const uint32_t a_addr = a_base + ((g.dbg & 4) ? (tap / 3) * 8 : ((tap / 3) * g.pitch + tap % 3)) * 128;   // dbg 4: 8-row aligned offsets (wrong results)
-          const uint32_t w_addr = w_base + tap * kWTile;
+        const uint32_t pitch8 = (uint32_t)g.pitch * 8u;            // one patch row = 128 B = 8 descriptor units
+        constexpr uint32_t idesc32 = ptx::idesc_bf16(128, 32);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if ((g.dbg & 2) && tap > 0) break;
+          const uint64_t a_tap = a_desc0 + (uint64_t)((g.dbg & 4) ? (tap / 3) * 64u : (tap / 3) * pitch8 + (tap % 3) * 8u);   // dbg 4: 8-row aligned offsets (wrong results)
+          const uint64_t w_tap = w_desc0 + (uint64_t)(tap * (kWTile / 16));
           if (g.dense || (g.dbg & 8)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + k * 32), idesc,
-                            (tap | k) != 0 ? 1u : 0u);
+              ptx::umma_f16(d_tmem, a_tap + 2 * k, w_tap + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
           } else {
             // grouped: the slice's [64 out x 64 in] tap matrix is block-diagonal (two groups of 32 channels), so k-steps
             // 0-1 (inputs of group 0) only feed output columns 0..31 and k-steps 2-3 columns 32..63: N = 32 MMAs on
-            // the matching 32 weight rows fetch half the B operand (the MMA is bound by its shared-memory operand reads)
-            constexpr uint32_t idesc32 = ptx::idesc_bf16(128, 32);
+            // the matching 32 weight rows
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t grp = k >> 1;
-              ptx::umma_f16(d_tmem + grp * 32, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(w_addr + grp * 32 * 128 + k * 32),
-                            idesc32, (tap | (k & 1)) != 0 ? 1u : 0u);
+              ptx::umma_f16(d_tmem + grp * 32, a_tap + 2 * k, w_tap + grp * (32 * 128 / 16) + 2 * k, idesc32, (tap | (k & 1)) != 0 ? 1u : 0u);
             }
           }
         }
