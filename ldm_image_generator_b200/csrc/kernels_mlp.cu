@@ -244,9 +244,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       constexpr uint32_t idesc1 = ptx::idesc_bf16(128 * CG, 128);
       constexpr uint32_t idesc2 = ptx::idesc_bf16(128 * CG, C);
       auto commit = [&](uint64_t* bar) { if (CG == 2) ptx::umma_commit_2sm(bar, 3); else ptx::umma_commit(bar); };
-      auto mma = [&](uint32_t d, uint32_t aa, uint32_t bb, uint32_t idesc, uint32_t acc) {
-        if (CG == 2) ptx::umma_f16_2sm(d, ptx::smem_desc_sw128(aa), ptx::smem_desc_sw128(bb), idesc, acc);
-        else ptx::umma_f16(d, ptx::smem_desc_sw128(aa), ptx::smem_desc_sw128(bb), idesc, acc);
+      // descriptors: built once per operand tile, (k-block, k) offsets ADDED in 16-byte units (the MMA thread is issue-bound:
+      // rebuilding both descriptors per tcgen05.mma cost ~21 SASS instructions each, see kernels_gconv.cu)
+      auto mma = [&](uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        if (CG == 2) ptx::umma_f16_2sm(d, adesc, bdesc, idesc, acc);
+        else ptx::umma_f16(d, adesc, bdesc, idesc, acc);
       };
       Ring ra, r1, r2, rd1, rd2;
       const uint32_t d2 = tmem_base + Cfg::D2_COL;
@@ -256,20 +258,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!wait_bar(&a1_full[ra.i], ra.ph, s_abort, fault, 24)) break;
         if (first_tile) trace_stamp(trace, 3);
         ptx::tc_fence_after();
-        const uint32_t a1_addr = ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES);
+        const uint64_t a1_desc = ptx::smem_desc_sw128(ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES));
         for (int s = 0; ok && s < UNITS + LAG; ++s) {
           if (s < UNITS) {
             if (!wait_bar(&d1_empty[rd1.i], rd1.ph ^ 1, s_abort, fault, 25)) { ok = false; break; }
             if (!wait_bar(&w1_full[r1.i], RES ? 0u : r1.ph, s_abort, fault, 26)) { ok = false; break; }   // RES: landed once, stays
             ptx::tc_fence_after();
             const uint32_t d1 = tmem_base + rd1.i * 128;
-            const uint32_t bb = ptx::smem_u32(w1 + r1.i * Cfg::W1_BYTES);
+            const uint64_t b1_desc = ptx::smem_desc_sw128(ptx::smem_u32(w1 + r1.i * Cfg::W1_BYTES));
             if (!(a.dbg & 4)) {
 #pragma unroll
               for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  mma(d1, a1_addr + kb * 16384 + k * 32, bb + kb * (Cfg::B1_ROWS * 128) + k * 32, idesc1, (kb | k) != 0 ? 1u : 0u);
+                  mma(d1, a1_desc + (kb * 16384 + k * 32) / 16, b1_desc + (kb * (Cfg::B1_ROWS * 128) + k * 32) / 16, idesc1, (kb | k) != 0 ? 1u : 0u);
             }
             commit(&g1_done[r1.i]);                               // -> epilogue (D1 full) and producer (W1 stage free)
             if (s == UNITS - 1) commit(&a1_empty[ra.i]);          // the xm tile has been consumed by all GEMM1 units
@@ -285,10 +287,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t w2i = RES ? (uint32_t)u : r2.i;
             if (!wait_bar(&w2_full[w2i], RES ? 0u : r2.ph, s_abort, fault, 29)) { ok = false; break; }
             ptx::tc_fence_after();
-            const uint32_t ha = ptx::smem_u32(hs + r2.i * Cfg::H_BYTES), bb = ptx::smem_u32(w2 + w2i * Cfg::W2_BYTES);
+            const uint64_t h_desc = ptx::smem_desc_sw128(ptx::smem_u32(hs + r2.i * Cfg::H_BYTES));
+            const uint64_t b2_desc = ptx::smem_desc_sw128(ptx::smem_u32(w2 + w2i * Cfg::W2_BYTES));
             if (!(a.dbg & 2)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d2, ha + k * 32, bb + k * 32, idesc2, (u | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) mma(d2, h_desc + 2 * k, b2_desc + 2 * k, idesc2, (u | k) != 0 ? 1u : 0u);
             }
             commit(&g2_done[r2.i]);                               // -> epilogue (h slot free) and producer (W2 stage free)
             r2.next(HS);

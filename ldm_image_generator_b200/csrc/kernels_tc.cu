@@ -240,15 +240,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           wait_bar(&full[stage], phase, s_abort, fault, 3);
           if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          // one descriptor per operand tile, k offsets added in 16-byte units (the MMA thread is issue-bound, see kernels_gconv.cu)
+          const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES));
+          const uint64_t b_desc = a_desc + Cfg::A_BYTES / 16;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (tl.dbg & 2) break;
-            if (CG == 2) ptx::umma_f16_2sm(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
-                                           (kb != kb0 || k != 0) ? 1u : 0u);
-            else ptx::umma_f16(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32), idesc,
-                               (kb != kb0 || k != 0) ? 1u : 0u);
+            if (CG == 2) ptx::umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            else ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]);
