@@ -128,15 +128,16 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && sp0 < sp_end) {
+    if (sp0 < sp_end) {   // the whole warp runs the loop (uniform control flow: descriptors stay in uniform registers); one elected lane issues
+      const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc = ptx::idesc_bf16(128, kSlice);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       bool ok = wait_bar(wbar, 0, s_abort, fault, 12);
-      trace_stamp(trace, 10);
+      if (issuer) trace_stamp(trace, 10);
       for (int sp = sp0; ok && sp < sp_end; sp += sp_step) {
         if (!wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 13)) break;
         if (!wait_bar(&full[stage], phase, s_abort, fault, 14)) break;
-        if (sp == sp0) trace_stamp(trace, 4);
+        if (sp == sp0 && issuer) trace_stamp(trace, 4);
         ptx::tc_fence_after();
         // The MMA thread is issue-bound (ncu: ~21 SASS instructions per tcgen05.mma, most of them building the two
         // shared-memory descriptors and moving them to uniform registers): the descriptors of a tile differ only in their
@@ -154,7 +155,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (g.dense || (g.dbg & 8)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(d_tmem, a_tap + 2 * k, w_tap + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+              if (issuer) ptx::umma_f16(d_tmem, a_tap + 2 * k, w_tap + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
           } else {
             // grouped: the slice's [64 out x 64 in] tap matrix is block-diagonal (two groups of 32 channels), so k-steps
             // 0-1 (inputs of group 0) only feed output columns 0..31 and k-steps 2-3 columns 32..63: N = 32 MMAs on
@@ -162,17 +163,17 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t grp = k >> 1;
-              ptx::umma_f16(d_tmem + grp * 32, a_tap + 2 * k, w_tap + grp * (32 * 128 / 16) + 2 * k, idesc32, (tap | (k & 1)) != 0 ? 1u : 0u);
+              if (issuer) ptx::umma_f16(d_tmem + grp * 32, a_tap + 2 * k, w_tap + grp * (32 * 128 / 16) + 2 * k, idesc32, (tap | (k & 1)) != 0 ? 1u : 0u);
             }
           }
         }
-        ptx::umma_commit(&empty[stage]);
-        ptx::umma_commit(&tfull[as]);
+        if (issuer) { ptx::umma_commit(&empty[stage]); ptx::umma_commit(&tfull[as]); }
+        __syncwarp();
         if (++stage == (uint32_t)g.stages) { stage = 0; phase ^= 1; }
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
-      trace_stamp(trace, 5);
+      if (issuer) trace_stamp(trace, 5);
     }
     __syncwarp();
   } else {

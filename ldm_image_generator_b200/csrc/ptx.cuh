@@ -81,6 +81,12 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {   // <= N gr
 template <int N> __device__ __forceinline__ void bulk_wait() {        // <= N groups not yet complete
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
