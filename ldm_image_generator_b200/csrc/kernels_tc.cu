@@ -228,7 +228,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0 && leader) {
+    if (leader) {
+      // The whole warp runs the loop (uniform control flow keeps descriptors, addresses and counters in uniform registers:
+      // back-to-back tcgen05.mma instead of ~20 SASS instructions per issue); one elected lane issues.
+      const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
@@ -238,26 +241,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = (t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           wait_bar(&full[stage], phase, s_abort, fault, 3);
-          if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 4);   // first operands landed
+          if (issuer && t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           // one descriptor per operand tile, k offsets added in 16-byte units (the MMA thread is issue-bound, see kernels_gconv.cu)
           const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES));
           const uint64_t b_desc = a_desc + Cfg::A_BYTES / 16;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if (tl.dbg & 2) break;
+            if ((tl.dbg & 2) || !issuer) continue;
             if (CG == 2) ptx::umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             else ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]);
+          if (issuer) { if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]); }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) ptx::umma_commit_2sm(&tfull[as], 3); else ptx::umma_commit(&tfull[as]);   // accumulator complete -> epilogue(s)
+        if (issuer) { if (CG == 2) ptx::umma_commit_2sm(&tfull[as], 3); else ptx::umma_commit(&tfull[as]); }   // accumulator complete -> epilogue(s)
+        __syncwarp();
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
-      trace_stamp(trace, 5);                                           // all MMAs issued
+      if (issuer) trace_stamp(trace, 5);                               // all MMAs issued
     }
     __syncwarp();
   } else {
