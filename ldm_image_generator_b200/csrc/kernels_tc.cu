@@ -146,15 +146,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool sel_k = d.sel == 2 || d.sel == 3;        // weight rows selected per K slot
   auto srow = [&](int q) { return d.sel == 3 ? q * d.sel_stride : (q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3))); };
   const int total_tiles = skip_block ? 0 : tl.total;
-  const bool is_producer = warp == 0 && lane == 0;
+  const bool is_producer = warp == 0;          // the producer warp waits for the previous kernel only after its weight prefetch
   if (!is_producer) {
     pdl_wait();
     if (threadIdx.x == 32) trace_stamp(trace, 2);              // previous kernel complete
   }
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp, uniform control flow; one elected lane issues)
+    {
+      const bool issuer = ptx::elect_one();
       auto b_coords = [&](int z, int n0, int kk, int& brow, int& bcol) {
         bcol = kk;
         if (sel_k) { brow = srow(kk / d.sel_span) + n0; bcol = kk % d.sel_span; }
@@ -173,16 +174,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
           for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
             uint8_t* b_dst = tiles + pre * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-            if (leader) ptx::mbar_arrive_expect_tx(&full[pre], Cfg::STAGE_BYTES * CG);
             int brow, bcol;
             b_coords(z, nt * BN, kb * BK, brow, bcol);
-            if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[pre], bcol, brow);
-            else ptx::tma_load_2d(b_dst, &tmB, &full[pre], bcol, brow);
+            if (issuer) {
+              if (leader) ptx::mbar_arrive_expect_tx(&full[pre], Cfg::STAGE_BYTES * CG);
+              if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[pre], bcol, brow);
+              else ptx::tma_load_2d(b_dst, &tmB, &full[pre], bcol, brow);
+            }
           }
         }
       }
+      __syncwarp();
       pdl_wait();
-      trace_stamp(trace, 2);                                     // previous kernel complete (producer's view)
+      if (issuer) trace_stamp(trace, 2);                         // previous kernel complete (producer's view)
       uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
         const int sp = t / tiles_per_split, ts = t % tiles_per_split;
@@ -204,23 +208,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-          if (leader && !b_done) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
           const int kk = kb * BK;
-          if (AMODE == AM_ROWS) {
-            if (CG == 2) ptx::tma_load_2d_2sm(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
-            else ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
-          } else {
-            const int tap = kk / d.cC, c0 = kk % d.cC;
-            if (CG == 2) ptx::tma_load_4d_2sm(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
-            else ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+          int brow = 0, bcol = 0;
+          if (!b_done) b_coords(z, n0, kk, brow, bcol);
+          const int tap = AMODE == AM_CONV3 ? kk / d.cC : 0, c0 = AMODE == AM_CONV3 ? kk % d.cC : 0;
+          if (issuer) {
+            if (leader && !b_done) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
+            if (AMODE == AM_ROWS) {
+              if (CG == 2) ptx::tma_load_2d_2sm(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
+              else ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
+            } else {
+              if (CG == 2) ptx::tma_load_4d_2sm(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+              else ptx::tma_load_4d(a_dst, &tmA, &full[stage], c0 + (int)(z * d.a_koff_b), w0 + tap % 3 - 1, h0 + tap / 3 - 1, b0);
+            }
+            if (!b_done) {
+              if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
+              else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
+            }
+            if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 3);   // first loads issued
           }
-          if (!b_done) {
-            int brow, bcol;
-            b_coords(z, n0, kk, brow, bcol);
-            if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
-            else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
-          }
-          if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 3);   // first loads issued
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
