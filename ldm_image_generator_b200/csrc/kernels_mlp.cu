@@ -240,13 +240,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA of a pair issues for both)
-    if (lane == 0 && leader) {
+    if (leader) {
+      // the whole warp runs the loop (uniform control flow: descriptors and ring state in uniform registers), one elected lane issues
+      const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc1 = ptx::idesc_bf16(128 * CG, 128);
       constexpr uint32_t idesc2 = ptx::idesc_bf16(128 * CG, C);
-      auto commit = [&](uint64_t* bar) { if (CG == 2) ptx::umma_commit_2sm(bar, 3); else ptx::umma_commit(bar); };
+      auto commit = [&](uint64_t* bar) { if (issuer) { if (CG == 2) ptx::umma_commit_2sm(bar, 3); else ptx::umma_commit(bar); } __syncwarp(); };
       // descriptors: built once per operand tile, (k-block, k) offsets ADDED in 16-byte units (the MMA thread is issue-bound:
       // rebuilding both descriptors per tcgen05.mma cost ~21 SASS instructions each, see kernels_gconv.cu)
       auto mma = [&](uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        if (!issuer) return;
         if (CG == 2) ptx::umma_f16_2sm(d, adesc, bdesc, idesc, acc);
         else ptx::umma_f16(d, adesc, bdesc, idesc, acc);
       };
@@ -256,7 +259,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       bool first_tile = true;
       for (int ti = next_active(0); ok && ti < my_tiles; ti = next_active(ti + 1)) {
         if (!wait_bar(&a1_full[ra.i], ra.ph, s_abort, fault, 24)) break;
-        if (first_tile) trace_stamp(trace, 3);
+        if (first_tile && issuer) trace_stamp(trace, 3);
         ptx::tc_fence_after();
         const uint64_t a1_desc = ptx::smem_desc_sw128(ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES));
         for (int s = 0; ok && s < UNITS + LAG; ++s) {
@@ -301,10 +304,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         commit(d2_full);
         rd2.next(1);
         ra.next(Cfg::A1_BUFS);
-        if (first_tile) trace_stamp(trace, 4);
+        if (first_tile && issuer) trace_stamp(trace, 4);
         first_tile = false;
       }
-      trace_stamp(trace, 5);
+      if (issuer) trace_stamp(trace, 5);
     }
     __syncwarp();
   } else {
