@@ -180,13 +180,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (CG == 2) ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool is_producer = warp == 0 && lane == 0;
+  const bool is_producer = warp == 0;          // the producer warp waits for the previous kernel after its weight prefetch
   if (threadIdx.x == 0) trace_stamp(trace, 1);
   if (!is_producer) pdl_wait();
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp, uniform control flow; one elected lane issues)
+    {
+      const bool issuer = ptx::elect_one();
       Ring ra, r1, r2;
       int n1 = 0, n2 = 0;                                   // next unit (counted over the active tiles of this CTA) of each weight ring
       int w1_ti = next_active(0), w2_ti = w1_ti;            // the tile those units belong to (its image picks the experts)
@@ -195,41 +196,53 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto issue_w1 = [&]() {
         const int u = n1 % UNITS, e = u / NKB, j = u % NKB;
         if (!RES && !wait_bar(&g1_done[r1.i], r1.ph ^ 1, s_abort, fault, 22)) { ok = false; return; }
-        if (leader) ptx::mbar_arrive_expect_tx(&w1_full[r1.i], Cfg::W1_BYTES * CG);
         const int row = slot_of(w1_ti, e) * 2 * C + j * 128 + (int)rank * Cfg::B1_ROWS;
-        for (int kb = 0; kb < NKB; ++kb) {
-          uint8_t* dst = w1 + r1.i * Cfg::W1_BYTES + kb * (Cfg::B1_ROWS * 128);
-          if (CG == 2) ptx::tma_load_2d_2sm(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
-          else ptx::tma_load_2d(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
+        if (issuer) {
+          if (leader) ptx::mbar_arrive_expect_tx(&w1_full[r1.i], Cfg::W1_BYTES * CG);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            uint8_t* dst = w1 + r1.i * Cfg::W1_BYTES + kb * (Cfg::B1_ROWS * 128);
+            if (CG == 2) ptx::tma_load_2d_2sm(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
+            else ptx::tma_load_2d(dst, &tmWab, &w1_full[r1.i], kb * 64, row);
+          }
         }
+        __syncwarp();
         r1.next(W1S);
         if (++n1 % UNITS == 0) w1_ti = next_active(w1_ti + 1);
       };
       auto issue_w2 = [&]() {
         const int u = n2 % UNITS, e = u / NKB, j = u % NKB;
         if (!RES && !wait_bar(&g2_done[r2.i], r2.ph ^ 1, s_abort, fault, 23)) { ok = false; return; }
-        if (leader) ptx::mbar_arrive_expect_tx(&w2_full[r2.i], Cfg::W2_BYTES * CG);
         const int row = slot_of(w2_ti, e) * C + (int)rank * Cfg::B2_ROWS;
-        if (CG == 2) ptx::tma_load_2d_2sm(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
-        else ptx::tma_load_2d(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
+        if (issuer) {
+          if (leader) ptx::mbar_arrive_expect_tx(&w2_full[r2.i], Cfg::W2_BYTES * CG);
+          if (CG == 2) ptx::tma_load_2d_2sm(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
+          else ptx::tma_load_2d(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
+        }
+        __syncwarp();
         r2.next(W2S);
         if (++n2 % UNITS == 0) w2_ti = next_active(w2_ti + 1);
       };
       // fill both weight rings while the previous kernel is still draining; only the xm tiles wait for it
       while (ok && w1_ti < my_tiles && n1 < W1S) issue_w1();
       while (ok && w2_ti < my_tiles && n2 < W2S) issue_w2();      // RES: W1S = W2S = UNITS -- every weight tile, once
+      __syncwarp();
       pdl_wait();
-      trace_stamp(trace, 2);
+      if (issuer) trace_stamp(trace, 2);
       int ta = 0;                                           // ordinal of the tile among this CTA's active tiles
       for (int ti = next_active(0); ok && ti < my_tiles; ti = next_active(ti + 1), ++ta) {
         const int m0 = (t0 + ti * t_step) * (128 * CG) + (int)rank * 128;
         if (!wait_bar(&a1_empty[ra.i], ra.ph ^ 1, s_abort, fault, 21)) break;
-        if (leader) ptx::mbar_arrive_expect_tx(&a1_full[ra.i], Cfg::A1_BYTES * CG);
-        for (int kb = 0; kb < NKB; ++kb) {
-          uint8_t* dst = a1 + ra.i * Cfg::A1_BYTES + kb * 16384;
-          if (CG == 2) ptx::tma_load_2d_2sm(dst, &tmX, &a1_full[ra.i], kb * 64, m0);
-          else ptx::tma_load_2d(dst, &tmX, &a1_full[ra.i], kb * 64, m0);
+        if (issuer) {
+          if (leader) ptx::mbar_arrive_expect_tx(&a1_full[ra.i], Cfg::A1_BYTES * CG);
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            uint8_t* dst = a1 + ra.i * Cfg::A1_BYTES + kb * 16384;
+            if (CG == 2) ptx::tma_load_2d_2sm(dst, &tmX, &a1_full[ra.i], kb * 64, m0);
+            else ptx::tma_load_2d(dst, &tmX, &a1_full[ra.i], kb * 64, m0);
+          }
         }
+        __syncwarp();
         ra.next(Cfg::A1_BUFS);
         for (int s = 0; !RES && ok && s < UNITS + LAG; ++s) {     // same order as the MMA thread consumes
           if (s < UNITS && ta * UNITS + s >= n1) issue_w1();
