@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""Graph-timed grouped 3x3 halo conv at the four level shapes of config 2 (LDMB_GCONV_DBG bits for A/B runs)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ldm_image_generator_b200 import runtime
 from tools.bench_kernels import timeit

@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0, "/root/repo")
+import os, sys, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, random
 from ldm_image_generator_b200 import DDPM, UNet
 torch.manual_seed(1234)
