@@ -14,10 +14,21 @@ noise seed 0, eval mode, eta=0.
   e2e    the same through the public module API with HOST buffers: pinned x_T -> device, sample, decode,
          uint8 images -> pinned host (+ the final NCCL all_gather of the images at N>1)
   roofline / kernels   per-kernel-class CUDA-event times of one extra (untimed) step, library-side events
-  cpu_baseline         the CPU oracle port on this box's host cores, bounded sample, rank 0 at N=1 only
+  cpu_baseline         the reference's CPU path on this box's host cores, bounded sample, rank 0 at N=1 only
+  gpu_baseline         the reference's own GPU path -- PyTorch eager on this B200, fp32 (TF32 off) and fp16 autocast
+                       (ddpm.py:75) -- on a bounded sample, outside the timed region, rank 0 at N=1 only
+  unet_steps_per_sec   batched UNet steps (one UNet.forward + DDIM update over the per-GPU batch) per second, whole job
 
-``--impl reference`` times the CPU implementation (oracle port of the reference's algorithm; the Python
-reference itself cannot travel to the GPU box) on a bounded sample per step and prints the same line shape.
+``--impl reference`` times the reference's CPU implementation on a bounded sample per step and prints the same line
+shape: the UNMODIFIED reference staged under oracle/_ref by oracle/make_ref.py (``kind: "reference"``) when it
+travelled with the snapshot, else the oracle port (``kind: "port"``, which evaluates the Encodings MLP once per batch
+instead of once per image: about 2x LESS work than the stock reference -- a conservative denominator).
+
+Other workloads of BASELINE.json (the driver runs the default):
+  --global-batch 512   configs[2] as a STRONG-scaling point: 512 images in total, 512/N per GPU ("scaling": "strong")
+  --config wide        configs[3]: UNet(channels=[256,512,1024,2048]) at latent 64x64, 16 images/GPU, --num-steps 1000
+                       DDIM steps, decode to 512x512
+  --config vae         configs[4]: VAE encode + decode round trip at 512x512, 256 images/GPU in micro-batches of 16
 """
 from __future__ import annotations
 
@@ -35,10 +46,17 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "images/sec (50-step LDM sampling + VAE decode, 256x256)"
-UNET_GFLOP_PER_IMAGE_STEP = 14.00      # hoisted algorithmic figure, SURVEY.md 8d
-UNET_GFLOP_ENCODINGS_PER_STEP = 19.33  # batch-invariant Encodings MLP, once per step
-DECODER_GFLOP_PER_IMAGE = 80.59
+# hoisted algorithmic GFLOP: per image-step, Encodings MLP once per step, decoder / encoder per image
+WORKLOADS = {
+    "base": dict(metric="images/sec (50-step LDM sampling + VAE decode, 256x256)", channels=[128, 256, 512, 1024], latent=32,
+                 batch=64, num_steps=50, unet_gf=14.00, enc_gf=19.33, dec_gf=80.59, px=256, params="385.7M",
+                 name="configs[1]: random-init LDM, default UNet"),
+    "wide": dict(metric="images/sec (1000-step LDM sampling, wide UNet, + VAE decode, 512x512)", channels=[256, 512, 1024, 2048],
+                 latent=64, batch=16, num_steps=1000, unet_gf=214.82, enc_gf=524.06 - 214.82, dec_gf=322.34, px=512,
+                 params="1.53B", name="configs[3]: random-init LDM, wide UNet (2x base channels)"),
+}
+VAE_METRIC = "images/sec (VAE encode+decode round trip, 512x512)"
+VAE_GF = 312.59 + 322.34
 
 
 def peaks():
@@ -89,68 +107,210 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-# ----------------------------------------------------------------------------------------- CPU arm
-def cpu_sample_once(sd_unet, ucfg, sd_dec, dcfg, R, num_steps: int, unet_batch: int, latent: int):
-    """One bounded sample of the workload on the host: one UNet step at batch `unet_batch` and one decode of one
-    image, extrapolated linearly (every step costs the same; nothing in the algorithm depends on batch size)."""
-    x = torch.randn(unet_batch, ucfg.input_channels, latent, latent)
-    t = torch.full((unet_batch,), 500, dtype=torch.long)
-    plan = R.draw_plan(len(R.block_table(ucfg)), False)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        R.unet_forward(sd_unet, ucfg, x, t, plan)
-    t1 = time.perf_counter()
-    with torch.no_grad():
-        R.decoder_forward(sd_dec, dcfg, x[:1])
-    t2 = time.perf_counter()
-    per_image = num_steps * (t1 - t0) / unet_batch + (t2 - t1)
-    return 1.0 / per_image, (t1 - t0), (t2 - t1)
+def host_threads() -> int:
+    """All the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
+    return torch.get_num_threads()
 
 
-def build_cpu_arm():
-    from oracle import restate as R     # the CPU arm being timed / the checker -- never the product path
-    from ldm_image_generator_b200 import Decoder, UNet
-    torch.manual_seed(1234)
-    u = UNet(); d = Decoder()
-    sd_u = {k: v.detach() for k, v in u.state_dict().items()}
-    sd_d = {k: v.detach() for k, v in d.state_dict().items()}
-    return R, sd_u, R.UNetCfg(), sd_d, R.DecoderCfg()
+# ----------------------------------------------------------------------------------------- the reference's own code paths
+class BaselineArm:
+    """The reference implementation of the path on a torch device: the unmodified reference from oracle/_ref
+    (``kind == "reference"``) or, when that did not travel, the oracle port (``kind == "port"``).  Never the product."""
+
+    def __init__(self, wl: dict, want_vae: bool = False):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        try:
+            import make_ref
+            mods = make_ref.import_reference()
+        finally:
+            sys.path.pop(0)
+        self.wl, self.mods = wl, mods
+        self.kind = "reference" if mods is not None else "port"
+        self.hoists = mods is None
+        torch.manual_seed(1234)
+        if mods is not None:
+            self.unet = mods["unet"].UNet(channels=list(wl["channels"])).eval()
+            self.dec = mods["vae"].Decoder().eval()
+            self.enc = mods["vae"].Encoder().eval() if want_vae else None
+            self.ddpm = mods["ddpm"].DDPM(model=self.unet).eval()
+        else:
+            from oracle import restate as R      # the CPU arm being timed / the checker -- never the product path
+            self.R = R
+            self.ucfg = R.UNetCfg(channels=tuple(wl["channels"]))
+            self.dcfg, self.ecfg = R.DecoderCfg(), R.EncoderCfg()
+            self.sd_u, self.sd_d = R.make_unet_state(self.ucfg, 1234), R.make_decoder_state(self.dcfg, 1234)
+            self.sd_e = R.make_encoder_state(self.ecfg, 1234) if want_vae else None
+        self.device = torch.device("cpu")
+
+    def to(self, device):
+        self.device = torch.device(device)
+        if self.mods is not None:
+            self.ddpm.to(self.device); self.dec.to(self.device)
+            if self.enc is not None:
+                self.enc.to(self.device)
+        else:
+            self.sd_u = {k: v.to(self.device) for k, v in self.sd_u.items()}
+            self.sd_d = {k: v.to(self.device) for k, v in self.sd_d.items()}
+        return self
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def unet_steps(self, batch: int, latent: int, n: int, autocast: bool = False) -> float:
+        """Seconds for n denoise steps (UNet forward + DDIM update) on `batch` images through the reference's sampler."""
+        self._sync()
+        t0 = time.perf_counter()
+        if self.mods is not None:
+            # stock code path: ddpm.py:52-93 (tqdm bar on stderr included); num_steps=n -> n UNet forwards
+            self.ddpm.sample(x_shape=(batch, 8, latent, latent), seed=0, num_steps=n, use_autocast=autocast)
+        else:
+            R = self.R
+            x = torch.randn(batch, 8, latent, latent, device=self.device)
+            with torch.no_grad():
+                for _ in range(n):
+                    t = torch.full((batch,), 500, dtype=torch.long, device=self.device)
+                    eps = R.unet_forward(self.sd_u, self.ucfg, x, t, R.draw_plan(len(R.block_table(self.ucfg)), False))
+                    x = x - 0.01 * eps
+        self._sync()
+        return time.perf_counter() - t0
+
+    def decode(self, batch: int, latent: int) -> float:
+        z = torch.randn(batch, 8, latent, latent, device=self.device)
+        self._sync()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.mods is not None:
+                self.dec(z)                       # sample_ldm.py:73-74
+            else:
+                self.R.decoder_forward(self.sd_d, self.dcfg, z)
+        self._sync()
+        return time.perf_counter() - t0
+
+    def roundtrip(self, batch: int, px: int) -> float:
+        img = torch.randn(batch, 3, px, px, device=self.device).clamp(-1, 1)
+        self._sync()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.mods is not None:
+                self.dec(self.enc(img))
+            else:
+                self.R.decoder_forward(self.sd_d, self.dcfg, self.R.encoder_forward(self.sd_e, self.ecfg, img))
+        self._sync()
+        return time.perf_counter() - t0
+
+    def describe(self) -> str:
+        if self.kind == "reference":
+            return "unmodified reference (oracle/_ref), fp32, Encodings MLP per image as the reference computes it"
+        return ("fp32 oracle port (oracle/restate.py) with the Encodings MLP evaluated once per batch -- NOT the stock "
+                "reference's work, about 2x less")
+
+
+def cpu_sample_once(arm: BaselineArm, args, ub: int = 4):
+    """One bounded sample of the workload on the host, extrapolated linearly (every step costs the same; nothing in
+    the algorithm depends on batch size): one denoise step at batch `ub` and one decode of one image."""
+    if args.config == "vae":
+        t = arm.roundtrip(1, 512)
+        return 1.0 / t, t, 0.0
+    t_u = arm.unet_steps(ub, args.latent, 1)
+    t_d = arm.decode(1, args.latent)
+    return 1.0 / (args.num_steps * t_u / ub + t_d), t_u, t_d
+
+
+def cpu_sample_text(arm: BaselineArm, args, n: int, last, ub: int = 4) -> str:
+    if args.config == "vae":
+        return f"{n} x (encode + decode of 1 image at 512x512), {arm.describe()} ({last[1]:.3f} s)"
+    return (f"{n} x (1 denoise step at batch {ub} + 1 decode of 1 image), {arm.describe()}, extrapolated linearly to "
+            f"{args.num_steps} steps/image (UNet {last[1]:.3f} s, decode {last[2]:.3f} s)")
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
-    R, sd_u, ucfg, sd_d, dcfg = build_cpu_arm()
+    cores = host_threads()
+    arm = BaselineArm(workload(args), want_vae=args.config == "vae")
     random.seed(0); torch.manual_seed(0)
-    ub = 4
     for _ in range(max(args.warmup, 0)):
-        cpu_sample_once(sd_u, ucfg, sd_d, dcfg, R, args.num_steps, ub, args.latent)
+        cpu_sample_once(arm, args)
     vals, t0 = [], time.perf_counter()
     for _ in range(args.steps):
-        vals.append(cpu_sample_once(sd_u, ucfg, sd_d, dcfg, R, args.num_steps, ub, args.latent))
+        vals.append(cpu_sample_once(arm, args))
     wall = time.perf_counter() - t0
     v = sum(x[0] for x in vals) / len(vals)
-    sample = (f"per step: 1 UNet forward at batch {ub} + 1 decode of 1 image, fp32, extrapolated linearly to "
-              f"{args.num_steps} DDIM steps per image (UNet {vals[-1][1]:.3f} s, decode {vals[-1][2]:.3f} s)")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    line = {"impl": "reference", "metric": metric_name(args), "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": v, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": arm.kind,
+                             "sample": "per step: " + cpu_sample_text(arm, args, 1, vals[-1])},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     args._emit_ready()
     print(json.dumps(line), flush=True)
 
 
+def gpu_baseline(args, dev) -> dict:
+    """The reference's own GPU path: PyTorch eager on this B200 (sample_ldm.py -d cuda; ddpm.py:75 autocast = fp16),
+    bounded: 3 denoise steps + one decode at the bench's per-GPU batch, extrapolated linearly in the step count."""
+    out = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        arm = BaselineArm(workload(args), want_vae=args.config == "vae").to(dev)
+        out["kind"], B, L, n = arm.kind, args.batch, args.latent, 3
+        for name, autocast in (("fp32_no_tf32", False), ("fp16_autocast", True)):
+            if arm.kind == "port" and autocast:
+                continue
+            # fp32 leg: TF32 off everywhere (the oracle rule, SURVEY.md 8c); autocast leg: torch defaults, as the stock script runs
+            torch.backends.cuda.matmul.allow_tf32 = False if not autocast else tf32[0]
+            torch.backends.cudnn.allow_tf32 = False if not autocast else tf32[1]
+            if args.config == "vae":
+                arm.roundtrip(4, 512)
+                t = arm.roundtrip(16, 512)
+                out[name] = {"value": round(16 / t, 2), "unit": "images/sec", "roundtrip_ms_per_16": round(1e3 * t, 2)}
+                continue
+            arm.unet_steps(B, L, 1, autocast)                        # warm-up (cuDNN / cuBLAS heuristics, allocator)
+            t_u = arm.unet_steps(B, L, n, autocast) / n
+            arm.decode(min(B, 8), L)
+            t_d = arm.decode(B, L)
+            out[name] = {"value": round(B / (args.num_steps * t_u + t_d), 2), "unit": "images/sec",
+                         "unet_step_ms": round(1e3 * t_u, 3), "decode_ms": round(1e3 * t_d, 2)}
+        out["sample"] = (f"{arm.describe()}, PyTorch {torch.__version__} eager on the same GPU: {n} denoise steps + 1 decode at batch "
+                         f"{args.batch}, extrapolated linearly to {args.num_steps} steps" if args.config != "vae" else
+                         f"{arm.describe()}, PyTorch eager on the same GPU: encode+decode of 16 images at 512x512")
+        del arm
+    except Exception as e:  # a baseline that cannot run must not take the bench line down with it
+        out["unavailable"] = f"{type(e).__name__}: {str(e)[:200]}"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+    return out
+
+
+def workload(args) -> dict:
+    return WORKLOADS["wide" if args.config == "wide" else "base"]
+
+
+def metric_name(args) -> str:
+    if args.config == "vae":
+        return VAE_METRIC
+    m = workload(args)["metric"]
+    return m.replace("50-step", f"{args.num_steps}-step").replace("1000-step", f"{args.num_steps}-step")
+
+
 def workload_config(args, n):
-    return {"workload": f"configs[1]: random-init LDM, default UNet (385.7M params) + default VAE Decoder (f=8), "
-                        f"{args.batch} images/GPU at 256x256, {args.num_steps} DDIM steps, eta=0, {args.mode} mode",
+    if args.config == "vae":
+        return {"workload": f"configs[4]: random-init default VAE Encoder + Decoder, round trip at 512x512, {args.batch} images/GPU in "
+                            f"micro-batches of {args.micro_batch}", "global_batch": args.batch * n, "per_gpu_batch": args.batch,
+                "sharding": "by image, no collective" if n > 1 else "single GPU",
+                "l2": "no flush: every activation tensor of a micro-batch (268 MB at 64 ch x 512^2 x 16 images) is larger than the 126 MB L2"}
+    wl = workload(args)
+    which = wl["name"] if not args.global_batch else "configs[2] (strong scaling): random-init LDM, default UNet"
+    return {"workload": f"{which} ({wl['params']} params) + default VAE Decoder (f=8), "
+                        f"{args.batch} images/GPU at {wl['px']}x{wl['px']}, {args.num_steps} DDIM steps, eta=0, {args.mode} mode",
             "global_batch": args.batch * n, "per_gpu_batch": args.batch, "latent": [8, args.latent, args.latent],
             "num_steps": args.num_steps, "sharding": "by image, no collective on the denoise path" if n > 1 else "single GPU",
             "l2": "no flush: 0.77 GB of bf16 weights + >100 MB of activations stream through the 126 MB L2 every UNet step"}
@@ -159,40 +319,76 @@ def workload_config(args, n):
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
-    from ldm_image_generator_b200 import DDPM, Decoder, UNet, parallel
+    from ldm_image_generator_b200 import DDPM, Decoder, Encoder, UNet, parallel
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    vae_cfg = args.config == "vae"
+    wl = workload(args)
     torch.manual_seed(1234)
-    unet = UNet(); dec = Decoder()
-    unet.to(dev); dec.to(dev)
-    unet.train(args.mode == "train"); dec.eval()
-    unet.set_precision(args.precision); dec.set_precision(args.precision)
-    ddpm = DDPM(model=unet)
     B, L = args.batch, args.latent
-    shape = (B, 8, L, L)
-    # identical seeds on every rank; each rank takes its slice of the full noise batch
-    x_host = parallel.shard_noise((B * world, 8, L, L), seed=0, rank=rank, world=world).pin_memory()
-    x_dev = x_host.to(dev)
-    out_host = torch.empty(B, 8 * L, 8 * L, 3, dtype=torch.uint8).pin_memory()
+    if vae_cfg:
+        enc = Encoder().to(dev).eval().set_precision(args.precision)
+        dec = Decoder().to(dev).eval().set_precision(args.precision)
+        handles = lambda: [enc._handle, dec._handle]                                        # noqa: E731
+        mb, px = args.micro_batch, 512
+        g = torch.Generator().manual_seed(rank)
+        img_host = torch.randn(B, 3, px, px, generator=g).clamp_(-1, 1).pin_memory()
+        img_dev = img_host.to(dev)
+        out_host = torch.empty(B, px, px, 3, dtype=torch.uint8).pin_memory()
+        h2d, d2h = img_host.numel() * 4, out_host.numel()
 
-    def step_device():
-        parallel.seed_plan_rng(0)       # same expert plan on every rank and every step (fixed workload)
-        z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=x_dev, progress=False)
-        return dec.decode_to_uint8(z)
+        def step_device():
+            last = None
+            for i in range(0, B, mb):
+                last = dec.decode_to_uint8(enc(img_dev[i:i + mb]))
+            return last
 
-    def step_e2e():
-        parallel.seed_plan_rng(0)
-        xd = x_host.to(dev, non_blocking=True)
-        z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=xd, progress=False)
-        u8 = dec.decode_to_uint8(z)
-        if world > 1:
-            parallel.gather_images(u8, B * world)      # the one collective of the path: final image gather over NVLink
-        out_host.copy_(u8, non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the caller holds the images when the step returns
-        return out_host
+        def step_e2e():
+            for i in range(0, B, mb):
+                x = img_host[i:i + mb].to(dev, non_blocking=True)
+                out_host[i:i + mb].copy_(dec.decode_to_uint8(enc(x)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_host
+        step_unet = None
+    else:
+        unet = UNet(channels=list(wl["channels"])); dec = Decoder()
+        unet.to(dev); dec.to(dev)
+        unet.train(args.mode == "train"); dec.eval()
+        unet.set_precision(args.precision); dec.set_precision(args.precision)
+        handles = lambda: [unet._handle, dec._handle]                                       # noqa: E731
+        ddpm = DDPM(model=unet)
+        shape = (B, 8, L, L)
+        # identical seeds on every rank; each rank takes its slice of the full noise batch
+        x_host = parallel.shard_noise((B * world, 8, L, L), seed=0, rank=rank, world=world).pin_memory()
+        x_dev = x_host.to(dev)
+        out_host = torch.empty(B, 8 * L, 8 * L, 3, dtype=torch.uint8).pin_memory()
+        h2d, d2h = x_host.numel() * 4, out_host.numel()
+
+        def step_unet():
+            parallel.seed_plan_rng(0)
+            return ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=x_dev, progress=False)
+
+        def step_device():
+            parallel.seed_plan_rng(0)       # same expert plan on every rank and every step (fixed workload)
+            z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=x_dev, progress=False)
+            return dec.decode_to_uint8(z)
+
+        def step_e2e():
+            parallel.seed_plan_rng(0)
+            xd = x_host.to(dev, non_blocking=True)
+            z = ddpm.sample(shape, seed=None, num_steps=args.num_steps, x_T=xd, progress=False)
+            u8 = dec.decode_to_uint8(z)
+            if world > 1:
+                parallel.gather_images(u8, B * world)      # the one collective of the path: final image gather over NVLink
+            out_host.copy_(u8, non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller holds the images when the step returns
+            return out_host
+
+    def launches_now():
+        return sum(h.launches for h in handles() if h is not None)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -202,7 +398,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = unet._handle.launches + dec._handle.launches
+        l0 = launches_now()
         e0.record()
         for _ in range(steps):
             fn()
@@ -213,7 +409,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), unet._handle.launches + dec._handle.launches - l0
+        return float(ms.item()), launches_now() - l0
 
     clocks = ClockSampler(local_rank)
     timed(step_device, 0, max(args.warmup, 3))        # warm-up (also sizes workspaces, uploads weights)
@@ -221,22 +417,26 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms, launches = timed(step_device, args.steps, 0)
     clk = clocks.stop()
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
-    assert unet._handle.device_fault() == 0 and dec._handle.device_fault() == 0, "tcgen05 watchdog fired"
+    ms_unet = timed(step_unet, args.steps, 1)[0] if step_unet is not None else None
+    for h in handles():
+        assert h.device_fault() == 0, "tcgen05 watchdog fired"
 
     # one extra, untimed step with library-side per-launch events -> per-kernel-class roofline
     pk = peaks()
-    unet._handle.profile_begin(); dec._handle.profile_begin()
+    for h in handles():
+        h.profile_begin()
     step_device()
-    pu, pd = unet._handle.profile_end(), dec._handle.profile_end()
+    profs = [h.profile_end() for h in handles()]
+    H0 = handles()[0]
     classes = {}
-    for name in pu:
-        m = pu[name][0] + pd[name][0]; w = pu[name][1] + pd[name][1]; n = pu[name][2] + pd[name][2]
+    for name in profs[0]:
+        m = sum(p[name][0] for p in profs); w = sum(p[name][1] for p in profs); n = sum(p[name][2] for p in profs)
         if n:
             classes[name] = {"ms": round(m, 3), "launches": n, "work": w}
     total_ms = sum(c["ms"] for c in classes.values()) or 1.0
     kernels = {}
     for name, c in classes.items():
-        tensor = name in unet._handle.TENSOR_CLASSES
+        tensor = name in H0.TENSOR_CLASSES
         ach = c["work"] / (c["ms"] * 1e-3) / (1e12 if tensor else 1e9) if c["ms"] > 0 and c["work"] > 0 else None
         kernels[name] = {"share": round(c["ms"] / total_ms, 4), "ms": c["ms"], "launches": c["launches"],
                          "achieved": None if ach is None else round(ach, 2), "unit": "TFLOP/s" if tensor else "GB/s"}
@@ -245,11 +445,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     peak = pk["tf_sustained"] if tensor else pk["hbm"]
     # DRAM traffic of the dominant class's most frequent launch, from the committed `ncu --set full` capture
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if os.path.exists(tp):
-        t = json.load(open(tp)).get(dom)
-        if t:
-            traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
+    for tp in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):
+            t = json.load(open(tp)).get(dom)
+            if t:
+                traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
+                break
     roofline = {"kernel": dom, "bound": "tensor" if tensor else "hbm", "achieved": kernels[dom]["achieved"], "peak": peak,
                 "unit": kernels[dom]["unit"], "frac": round(kernels[dom]["achieved"] / peak, 4), "traffic": traffic,
                 "traffic_note": traffic_note,
@@ -259,11 +461,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # The per-launch events above serialise the launches (no programmatic-dependent-launch overlap) and include each
     # launch's latency.  What the dominant class costs INSIDE the graph-replayed step: the timed step with the class's
     # launches dropped (ldmb_debug_skip_classes: results are garbage, the launch sequence and timing are not), subtracted.
-    if dom in unet._handle.PROFILE_CLASSES and not dom.startswith("vae"):
+    if not vae_cfg and dom in H0.PROFILE_CLASSES and not dom.startswith("vae"):
         t_full, _ = timed(step_device, 2, 1)
-        unet._handle.skip_classes([dom])
+        H0.skip_classes([dom])
         t_skip, _ = timed(step_device, 2, 2)
-        unet._handle.skip_classes([])
+        H0.skip_classes([])
         timed(step_device, 0, 1)
         marginal_ms = (t_full - t_skip) / 2
         if marginal_ms > 0:
@@ -280,33 +482,40 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     images = B * world * args.steps
     value = images / (ms * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
-    alg_tflop = (B * (args.num_steps * UNET_GFLOP_PER_IMAGE_STEP + DECODER_GFLOP_PER_IMAGE)
-                 + args.num_steps * UNET_GFLOP_ENCODINGS_PER_STEP) / 1e3
-    line = {"metric": METRIC, "value": round(value, 3), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+    if vae_cfg:
+        alg_tflop = B * VAE_GF / 1e3
+    else:
+        alg_tflop = (B * (args.num_steps * wl["unet_gf"] + wl["dec_gf"]) + args.num_steps * wl["enc_gf"]) / 1e3
+    line = {"metric": metric_name(args), "value": round(value, 3), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic", "config": workload_config(args, world),
-            "e2e": {"value": round(e2e_value, 3), "unit": "images/sec", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel(), "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "e2e": {"value": round(e2e_value, 3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": kernels,
             "whole_step": {"algorithmic_tflop_per_gpu_step": round(alg_tflop, 2),
                            "achieved_tflops_per_gpu": round(alg_tflop / (ms / args.steps * 1e-3), 1),
                            "frac_of_sustained_bf16_peak": round(alg_tflop / (ms / args.steps * 1e-3) / pk["tf_sustained"], 4)}}
+    if ms_unet is not None:
+        # BASELINE.json's second metric: batched UNet steps per second (each step = UNet.forward + DDIM update on the per-GPU
+        # batch), whole job = sum over the GPUs; the sampling loop alone, decode excluded
+        sps = world * args.num_steps * args.steps / (ms_unet * 1e-3)
+        line["unet_steps_per_sec"] = {"value": round(sps, 2), "per_gpu_batch": B, "ms_per_unet_step": round(ms_unet / args.steps / args.num_steps, 4),
+                                      "image_steps_per_sec": round(sps * B, 1)}
     if world == 1 and not args.no_cpu_baseline:
-        try:
-            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-        except Exception:
-            pass
-        R, sd_u, ucfg, sd_d, dcfg = build_cpu_arm()
-        cpu_sample_once(sd_u, ucfg, sd_d, dcfg, R, args.num_steps, 4, L)
+        cores = host_threads()
+        arm = BaselineArm(wl, want_vae=vae_cfg)
+        cpu_sample_once(arm, args)
         t0, vals = time.perf_counter(), []
-        while time.perf_counter() - t0 < 12.0 and len(vals) < 8:
-            vals.append(cpu_sample_once(sd_u, ucfg, sd_d, dcfg, R, args.num_steps, 4, L))
+        while time.perf_counter() - t0 < 15.0 and len(vals) < 8:
+            vals.append(cpu_sample_once(arm, args))
         v = sum(x[0] for x in vals) / len(vals)
-        line["cpu_baseline"] = {"value": round(v, 5), "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{len(vals)} x (1 UNet forward at batch 4 + 1 decode of 1 image), fp32 oracle port with the "
-                                          f"Encodings MLP evaluated once per batch, extrapolated to {args.num_steps} steps/image "
-                                          f"(UNet {vals[-1][1]:.3f} s, decode {vals[-1][2]:.3f} s)"}
+        line["cpu_baseline"] = {"value": round(v, 5), "unit": "images/sec", "cores": cores, "kind": arm.kind,
+                                "sample": cpu_sample_text(arm, args, len(vals), vals[-1])}
+        del arm
+    if world == 1 and not args.no_gpu_baseline:
+        line["gpu_baseline"] = gpu_baseline(args, dev)
     args._emit_ready()
     print(json.dumps(line), flush=True)
     os.dup2(2, 1)
@@ -320,16 +529,30 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="base", choices=["base", "wide", "vae"])
     ap.add_argument("--mode", default="eval", choices=["eval", "train"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
-    ap.add_argument("--num-steps", type=int, default=50)
-    ap.add_argument("--latent", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the workload's)")
+    ap.add_argument("--global-batch", type=int, default=0, help="total images, split evenly over the GPUs (strong scaling)")
+    ap.add_argument("--micro-batch", type=int, default=16, help="--config vae: images per encode/decode call")
+    ap.add_argument("--num-steps", type=int, default=None)
+    ap.add_argument("--latent", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    wl = workload(args)
+    n = max(world, args.gpus if args.impl == "reference" else world)
+    if args.global_batch:
+        assert args.config == "base" and args.global_batch % max(args.gpus, 1) == 0, "--global-batch: base config, divisible by --gpus"
+        args.batch = args.global_batch // max(args.gpus, 1)
+    if args.batch is None:
+        args.batch = 256 if args.config == "vae" else wl["batch"]
+    args.num_steps = args.num_steps or wl["num_steps"]
+    args.latent = args.latent or wl["latent"]
+    del n
     args._emit_ready = lambda: None
     if args.impl == "reference":
         run_reference(args, rank)

@@ -111,6 +111,9 @@ int ldmb_set_deterministic(ldmb_handle* h, int on);
 int64_t ldmb_launch_count(const ldmb_handle* h);
 /* 0, or the watchdog code a tcgen05 pipeline wrote when an mbarrier wait timed out (device read; synchronises). */
 int ldmb_check_device_fault(ldmb_handle* h, void* stream);
+/* The same word through its host-mapped mirror: no synchronisation, so it only reflects kernels that have already run.
+ * Once it is non-zero every later ldmb_unet_* / ldmb_vae_* compute call on the handle returns LDMB_ERR_KERNEL. */
+int ldmb_poll_device_fault(const ldmb_handle* h);
 
 /* Debug: %globaltimer stamps inside the tcgen05 kernel.  stamps_host == NULL: enable/disable recording.
  * Otherwise copies 16 int64 stamps per CTA of the most recent tcgen05 launch (synchronises) and returns the CTA count:

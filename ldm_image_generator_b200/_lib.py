@@ -48,6 +48,7 @@ SIGNATURES = {
     "ldmb_set_use_graphs": (C.c_int, [_H, C.c_int]),
     "ldmb_launch_count": (C.c_int64, [_H]),
     "ldmb_check_device_fault": (C.c_int, [_H, _P]),
+    "ldmb_poll_device_fault": (C.c_int, [_H]),
     "ldmb_debug_tc_trace": (C.c_int, [_H, C.c_int, _I64P, C.c_int]),
     "ldmb_unet_forward_per_image": (C.c_int, [_H, _P, _P, C.c_int, C.c_int, C.c_int, _I32P, C.c_int, C.POINTER(_P), _I32P,
                                               C.POINTER(DdimCoef), _P, _P]),

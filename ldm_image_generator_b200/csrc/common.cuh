@@ -78,6 +78,15 @@ __device__ __forceinline__ bool resolve_plan(GemmDesc& d) {
   return false;
 }
 
+// A pipeline watchdog fired: record the first fault code in device memory and mirror it to the host-mapped word whose
+// address sits at fault[2..3] (tc_context.h), so the host sees it without synchronising.
+__device__ __forceinline__ void report_fault(int* fault, int code) {
+  if (atomicCAS(fault, 0, code) == 0) {
+    volatile int* host = *reinterpret_cast<volatile int* const*>(fault + 2);
+    if (host != nullptr) { *host = code; __threadfence_system(); }
+  }
+}
+
 // ---- programmatic dependent launch (PDL): every kernel of the library is launched with the stream-serialization
 // attribute and starts with pdl_wait(), so its launch latency / prologue overlaps the tail of the previous kernel.
 // griddepcontrol.wait blocks until the preceding kernel has completed and its writes are visible; it is a no-op

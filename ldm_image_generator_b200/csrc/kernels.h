@@ -13,7 +13,11 @@ TcContext* tc_context_create(int device, char* err, int errlen);
 void tc_context_destroy(TcContext*);
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s);
 bool tc_supported(const GemmDesc& d);
-int tc_read_fault(TcContext* ctx, cudaStream_t s);
+int tc_read_fault(TcContext* ctx, cudaStream_t s);   // synchronises `s`
+int tc_poll_fault(const TcContext* ctx);              // host-mapped mirror: no synchronisation (faults of kernels that have run)
+// true when launch_gemm_tc would update d.out (EPI_ACCUM_F32) through TMA reduce-adds only -- the precondition for running
+// another updater of the same tensor concurrently (the forked grouped conv)
+bool tc_accum_is_reduction(const GemmDesc& d);
 void tc_set_splitk(TcContext* ctx, bool on);
 // debug: per-CTA %globaltimer stamps (16 slots per CTA) of the most recent tcgen05 launch
 int tc_trace_enable(TcContext* ctx, int on);

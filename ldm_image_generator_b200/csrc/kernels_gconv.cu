@@ -47,7 +47,7 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatil
     if (*s_abort) return false;
     if (clock64() - t0 > 3000000000LL) {
       *s_abort = 1;
-      atomicCAS(fault, 0, code);
+      report_fault(fault, code);
       return false;
     }
   }
@@ -298,7 +298,7 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
   if (g.stages > 4) g.stages = 4;
   if (g.stages < 1) return cudaErrorNotSupported;
 
-  g.dbg = getenv("LDMB_GCONV_DBG") ? atoi(getenv("LDMB_GCONV_DBG")) : 0;
+  g.dbg = tc_knobs().gconv_dbg;
   CUtensorMap tmA, tmW;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   {
@@ -318,11 +318,11 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
       return cudaErrorInvalidValue;
   }
   const int smem = 1024 + kWBytes + g.stages * g.stage_bytes + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(gconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr.mark(ctx->device);
   }
   const int nz = C / kSlice;
   const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;

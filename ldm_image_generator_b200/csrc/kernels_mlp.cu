@@ -72,7 +72,7 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatil
     if (*s_abort) return false;
     if (clock64() - t0 > 3000000000LL) {
       *s_abort = 1;
-      atomicCAS(fault, 0, code);
+      report_fault(fault, code);
       return false;
     }
   }
@@ -435,11 +435,11 @@ template <int C, int CG, bool RES>
 cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMap& tmWab, const CUtensorMap& tmWc, const CUtensorMap& tmO,
                         const MlpArgs& a, cudaStream_t st) {
   using Cfg = MlpCfg<C, CG, RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, CG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr.mark(ctx->device);
   }
   int grid = a.m_tiles * CG < ctx->num_sms ? a.m_tiles * CG : (ctx->num_sms / CG) * CG;
   cudaLaunchConfig_t cfg;
@@ -490,7 +490,7 @@ cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, c
   a.b_ab = b_ab; a.b_c = b_c; a.plan = plan; a.e1 = e1; a.e2 = e2; a.M = M;
   a.plan_img = plan_img; a.rows_per_image = rows_per_image;
   a.m_tiles = (M + 128 * cg - 1) / (128 * cg);
-  a.dbg = getenv("LDMB_MLP_DBG") ? atoi(getenv("LDMB_MLP_DBG")) : 0;
+  a.dbg = tc_knobs().mlp_dbg;
   CUtensorMap tmX, tmWab, tmWc, tmO;
   const cuuint32_t ones[2] = {1, 1};
   auto enc = [&](CUtensorMap* tm, CUtensorMapDataType dt, const void* p, cuuint64_t cols, cuuint64_t rows, int esz, cuuint32_t bc, cuuint32_t br) {

@@ -70,7 +70,7 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, volatil
     if (*s_abort) return;
     if (clock64() - t0 > 3000000000LL) {   // ~1.5 s at 2 GHz: pipeline is stuck, drain instead of hanging
       *s_abort = 1;
-      atomicCAS(fault, 0, code);
+      report_fault(fault, code);
       return;
     }
   }
@@ -639,11 +639,19 @@ bool tc_supported(const GemmDesc& d) {
   return pick_bn(d, 148) != 0;
 }
 
+// Mirrors launch_gemm_tc's choice of the smem-staged TMA epilogue for an accumulate-into-the-residual GEMM.
+bool tc_accum_is_reduction(const GemmDesc& d) {
+  if (d.epi != EPI_ACCUM_F32 || !tc_supported(d)) return false;
+  const int batch = d.batch > 0 ? d.batch : 1;
+  return d.res == nullptr && batch == 1 && d.N % 32 == 0 && (d.ldo * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) % 16) == 0;
+}
+
 TcContext* tc_context_create(int device, char* err, int errlen) {
   TcContext* ctx = new TcContext();
   ctx->device = device;
   ctx->encode = nullptr;
   ctx->fault_dev = nullptr;
+  ctx->fault_host = nullptr;
   ctx->trace_dev = nullptr;
   ctx->splitk = true;
   void* fn = nullptr;
@@ -664,15 +672,27 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
     return nullptr;
   }
   ctx->num_sms = prop.multiProcessorCount;
-  e = cudaMalloc(&ctx->fault_dev, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(ctx->fault_dev, 0, sizeof(int));
+  e = cudaMalloc(&ctx->fault_dev, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->fault_dev, 0, 4 * sizeof(int));
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaMalloc(fault flag): %s", cudaGetErrorString(e)); delete ctx; return nullptr; }
+  // host-mapped mirror of the fault word: polled by every API call without a synchronisation (LDMB_ERR_KERNEL)
+  int* fh = nullptr;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&fh), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *fh = 0;
+    int* fh_dev = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&fh_dev), fh, 0) == cudaSuccess) {
+      const unsigned long long addr = reinterpret_cast<unsigned long long>(fh_dev);
+      if (cudaMemcpy(ctx->fault_dev + 2, &addr, sizeof(addr), cudaMemcpyHostToDevice) == cudaSuccess) ctx->fault_host = fh;
+    }
+    if (!ctx->fault_host) cudaFreeHost(fh);
+  }
   return ctx;
 }
 
 void tc_context_destroy(TcContext* ctx) {
   if (!ctx) return;
   if (ctx->fault_dev) cudaFree(ctx->fault_dev);
+  if (ctx->fault_host) cudaFreeHost(const_cast<int*>(ctx->fault_host));
   if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   delete ctx;
 }
@@ -697,6 +717,8 @@ int tc_trace_read(TcContext* ctx, long long* host, int max_ctas) {
 
 void tc_set_splitk(TcContext* ctx, bool on) { ctx->splitk = on; }
 
+int tc_poll_fault(const TcContext* ctx) { return ctx->fault_host ? *ctx->fault_host : 0; }
+
 int tc_read_fault(TcContext* ctx, cudaStream_t s) {
   int v = 0;
   if (cudaMemcpyAsync(&v, ctx->fault_dev, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
@@ -708,14 +730,14 @@ template <int BN, int AMODE, int CG>
 static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                                   const GemmDesc& d, const TcTiling& tl, cudaStream_t s) {
   using Cfg = TcCfg<BN, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr.mark(ctx->device);
   }
   int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
-  if (getenv("LDMB_TC_GRID") && atoi(getenv("LDMB_TC_GRID")) < grid) grid = (atoi(getenv("LDMB_TC_GRID")) / CG) * CG;   // debug
+  if (tc_knobs().grid > 0 && tc_knobs().grid < grid) grid = (tc_knobs().grid / CG) * CG;   // debug
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
@@ -735,8 +757,22 @@ static cudaError_t launch_tc_bn(TcContext* ctx, int bn, const CUtensorMap& tmA, 
   return launch_tc_inst<64, AMODE, CG>(ctx, tmA, tmB, tmO, d, tl, s);
 }
 
-static int g_tc_splitk = getenv("LDMB_NO_SPLITK") ? 0 : 1;
-static int g_tc_force_cg = getenv("LDMB_TC_CG") ? atoi(getenv("LDMB_TC_CG")) : 0;   // debug: 1 or 2 forces the CTA-group size
+const TcKnobs& tc_knobs() {
+  static const TcKnobs k = [] {
+    auto geti = [](const char* n, int dflt) { const char* v = getenv(n); return v ? atoi(v) : dflt; };
+    TcKnobs t;
+    t.grid = geti("LDMB_TC_GRID", 0);          // debug: cap the persistent grid
+    t.stages = geti("LDMB_TC_STAGES", 0);      // debug: use only this many smem pipeline stages
+    t.dbg = geti("LDMB_TC_DBG", 0);            // debug bits, see TcTiling::dbg
+    t.splits = geti("LDMB_TC_SPLITS", 0);      // debug: force the split-K factor
+    t.force_cg = geti("LDMB_TC_CG", 0);        // debug: 1 or 2 forces the CTA-group size
+    t.no_splitk = getenv("LDMB_NO_SPLITK") != nullptr;
+    t.mlp_dbg = geti("LDMB_MLP_DBG", 0);
+    t.gconv_dbg = geti("LDMB_GCONV_DBG", 0);
+    return t;
+  }();
+  return k;
+}
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   if (!tc_supported(d)) return cudaErrorNotSupported;
@@ -751,15 +787,15 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   // (The residual GEMMs used the same rule while the issuing thread was the bound; with the warp-uniform issue loops
   // pairs + split-K measure 1.3 % faster end to end.)
   if (d.epi == EPI_UPADD && (long long)((d.M + BM - 1) / BM) * ((d.N + bn - 1) / bn) * batch <= ctx->num_sms) cg = 1;
-  if (g_tc_force_cg == 1 || g_tc_force_cg == 2) cg = g_tc_force_cg;
+  if (tc_knobs().force_cg == 1 || tc_knobs().force_cg == 2) cg = tc_knobs().force_cg;
   TcTiling tl;
   tl.m_tiles = (d.M + BM * cg - 1) / (BM * cg);
   tl.n_tiles = (d.N + bn - 1) / bn;
   tl.num_kb = d.K / BK;
   tl.total = tl.m_tiles * tl.n_tiles * batch;
   tl.splits = 1; tl.kb_per = tl.num_kb;
-  tl.max_stages = getenv("LDMB_TC_STAGES") ? atoi(getenv("LDMB_TC_STAGES")) : 0;
-  tl.dbg = getenv("LDMB_TC_DBG") ? atoi(getenv("LDMB_TC_DBG")) : 0;
+  tl.max_stages = tc_knobs().stages;
+  tl.dbg = tc_knobs().dbg;
   tl.TW = tl.TH = tl.TB = 0;
 
   CUtensorMap tmA, tmB;
@@ -845,11 +881,11 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
   // split-K: an accumulate-into-the-residual GEMM with too few output tiles to fill the machine (deep UNet levels:
   // M = 1024..4096 rows, K = 3C..4C) is cut along K; every slice reduce-adds its partial tile into x with TMA.
   // (EPI_UPADD scatters its partial tiles with red.global.add: just as linear)
-  if (((tl.tma_out && d.epi == EPI_ACCUM_F32) || d.epi == EPI_UPADD) && g_tc_splitk && ctx->splitk) {
+  if (((tl.tma_out && d.epi == EPI_ACCUM_F32) || d.epi == EPI_UPADD) && !tc_knobs().no_splitk && ctx->splitk) {
     const int base = tl.total * cg;
     int sp = ctx->num_sms / (base > 0 ? base : 1);
     if (sp > tl.num_kb / 4) sp = tl.num_kb / 4;              // at least 4 k-blocks (K = 256) per slice
-    if (getenv("LDMB_TC_SPLITS")) sp = atoi(getenv("LDMB_TC_SPLITS"));   // debug
+    if (tc_knobs().splits > 0) sp = tc_knobs().splits;   // debug
     if (sp > 1) {
       tl.kb_per = (tl.num_kb + sp - 1) / sp;
       tl.splits = (tl.num_kb + tl.kb_per - 1) / tl.kb_per;

@@ -82,7 +82,7 @@ struct UNetState {
   float *w_first = nullptr, *b_first = nullptr, *w_last = nullptr, *b_last = nullptr;
   std::set<std::string> missing;
   Arena arena;
-  DevBuf xm, hbuf, qkv, pooled, stepbuf, te_pre, backup;
+  DevBuf xm, hbuf, qkv, pooled, stepbuf, te_pre, backup, pe_tmp;
   const int* plan_img_dev = nullptr;   // per-image plans [n_blocks][B] (skip | e1 << 8 | e2 << 16), NULL in the shared-plan mode
   bool per_image_ws = false;           // workspaces sized for the per-image path (hbuf 6C wide, skip backup)
   // FiLM tables precomputed for a whole schedule (ldmb_unet_precompute_film): film holds n_t = film_nt timesteps
@@ -162,6 +162,14 @@ int fail(ldmb_handle* h, int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+// A pipeline watchdog fired in an earlier kernel of this handle: every later compute call refuses with LDMB_ERR_KERNEL
+// (the results since then are garbage).  Read from the host-mapped mirror of the fault word: no synchronisation.
+#define CHECK_FAULT()                                                                              \
+  do {                                                                                             \
+    const int f__ = tc_poll_fault(h->tc);                                                          \
+    if (f__ != 0) return fail(h, LDMB_ERR_KERNEL, "a tcgen05 pipeline watchdog fired earlier on this handle (code %d)", f__); \
+  } while (0)
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -298,7 +306,7 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
   UNetState& u = h->unet;
   u.arena.release();
   for (auto& l : u.levels) { release(l.pe); release(l.xs); release(l.emb); release(l.h1); release(l.film); release(l.te); }
-  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.stepbuf); release(u.te_pre); release(u.backup);
+  release(u.xm); release(u.hbuf); release(u.qkv); release(u.pooled); release(u.stepbuf); release(u.te_pre); release(u.backup); release(u.pe_tmp);
   for (auto& g : u.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (u.cap_stream) cudaStreamDestroy(u.cap_stream);
   if (u.side_stream) cudaStreamDestroy(u.side_stream);
@@ -316,7 +324,12 @@ extern "C" void ldmb_destroy(ldmb_handle* h) {
 
 extern "C" const char* ldmb_last_error(const ldmb_handle* h) { return h ? h->err : "null handle"; }
 extern "C" int ldmb_precision_of(const ldmb_handle* h) { return h ? h->precision : -1; }
-extern "C" int ldmb_set_force_simt(ldmb_handle* h, int on) { if (!h) return LDMB_ERR_INVALID; h->force_simt = on != 0; return LDMB_OK; }
+extern "C" int ldmb_set_force_simt(ldmb_handle* h, int on) {
+  if (!h) return LDMB_ERR_INVALID;
+  h->force_simt = on != 0;
+  h->unet.ws_epoch++;          // captured graphs hold the old launch set
+  return LDMB_OK;
+}
 extern "C" int64_t ldmb_launch_count(const ldmb_handle* h) { return h ? h->launches : 0; }
 extern "C" int ldmb_debug_tc_trace(ldmb_handle* h, int enable, int64_t* stamps_host, int max_ctas) {
   if (!h) return -1;
@@ -355,6 +368,7 @@ extern "C" int ldmb_check_device_fault(ldmb_handle* h, void* stream) {
   if (!h) return -1;
   return tc_read_fault(h->tc, static_cast<cudaStream_t>(stream));
 }
+extern "C" int ldmb_poll_device_fault(const ldmb_handle* h) { return h ? tc_poll_fault(h->tc) : -1; }
 
 // =====================================================================================
 // UNet: configure + parameters
@@ -631,13 +645,11 @@ extern "C" int ldmb_unet_set_position_table(ldmb_handle* h, int level, const flo
   const size_t n = (size_t)C * Hl * Wl;
   int rc;
   if ((rc = ensure(h, L.pe, n * 4))) return rc;
-  float* tmp = nullptr;   // [C,H,W] staging -> transposed to [HW,C]
-  CK(cudaMalloc(&tmp, n * 4));
-  CK(cudaMemcpyAsync(tmp, pe_host, n * 4, cudaMemcpyHostToDevice, st));
-  rc = repack(h, tmp, L.pe.p, false, Hl * Wl, C, 1, 1, (long long)Hl * Wl, 0, C, 1, 0, st);
-  CK(cudaStreamSynchronize(st));   // pe_host and tmp may go away when we return
-  CK(cudaFree(tmp));
-  if (rc) return rc;
+  // [C,H,W] -> [HW,C] through a library-owned scratch (grows like any workspace; no allocation / synchronisation per call).
+  // pe_host is pageable host memory: cudaMemcpyAsync has staged it when it returns, so the caller may free it.
+  if ((rc = ensure(h, u.pe_tmp, n * 4))) return rc;
+  CK(cudaMemcpyAsync(u.pe_tmp.p, pe_host, n * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = repack(h, static_cast<const float*>(u.pe_tmp.p), L.pe.p, false, Hl * Wl, C, 1, 1, (long long)Hl * Wl, 0, C, 1, 0, st))) return rc;
   L.peH = Hl; L.peW = Wl;
   return LDMB_OK;
 }
@@ -661,7 +673,23 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // grouped 3x3 (unet.py:30): x += conv(xm); the residual stream is only ever added to (x itself is not read),
   // so the conv is forked onto the side stream and joined at the end of the block
   // (only where every concurrent update of x is an L2 reduction: halo conv reds, TMA reduce-add GEMM epilogues)
-  const bool fork = u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C);
+  const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
+  const bool fused_ffn = h->bf16() && !h->force_simt && mlp_fused_supported(M, C);
+  // the block's GEMM that updates x beside the forked conv: out_proj behind the fused feed-forward (attention blocks only),
+  // else the K-concatenated c-projection
+  GemmDesc c = gd();
+  if (fused_ffn) {   // x += att . W_out^T + b_out   (attention.py:82 out_proj; unet.py:44,47)
+    c.A = toff(h, u.hbuf.p, 3LL * C); c.lda = ldh; c.W = toff(h, w.w_c, 5LL * C * C); c.ldw = C; c.bias = w.b_c + 5LL * C;
+    c.out = x; c.ldo = C; c.M = M; c.N = C; c.K = C; c.epi = EPI_ACCUM_F32; c.plan = pl;
+  } else {           // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases      (unet.py:44,47: ffn and attention in one update)
+    c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
+    c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32;
+    c.sel = 2; c.sel_span = C; c.sel_stride = C; c.plan = pl;
+  }
+  // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
+  // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
+  const bool fork = u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
+                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c));
   if (fork) {
     if (!u.side_stream) {
       CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
@@ -673,7 +701,6 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false))) return rc;
     CK(cudaEventRecord(u.ev_join, u.side_stream));
   } else if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
-  const int ldh = 4 * C;                                   // hbuf row: [h_general | h_e1 | h_e2 | attention]
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
@@ -685,16 +712,11 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
                                  global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, pl, st));
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
-  if (h->bf16() && !h->force_simt && mlp_fused_supported(M, C)) {
+  if (fused_ffn) {
     // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM
     CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
          launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st));
-    if (w.attn) {   // x += att . W_out^T + b_out   (attention.py:82 out_proj; unet.py:44,47)
-      GemmDesc c = gd();
-      c.A = toff(h, u.hbuf.p, 3LL * C); c.lda = ldh; c.W = toff(h, w.w_c, 5LL * C * C); c.ldw = C; c.bias = w.b_c + 5LL * C;
-      c.out = x; c.ldo = C; c.M = M; c.N = C; c.K = C; c.epi = EPI_ACCUM_F32; c.plan = pl;
-      if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
-    }
+    if (w.attn && (rc = gemm(h, c, st, PK_FFN_C))) return rc;
     if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
     return LDMB_OK;
   }
@@ -704,11 +726,6 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_stride = 2 * C; d.plan = pl;
     if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
-    // x += [h_g|h_e1|h_e2|att] . [Wc_g|Wc_e1|Wc_e2|W_out]^T + biases      (unet.py:44,47: ffn and attention in one update)
-    GemmDesc c = gd();
-    c.A = u.hbuf.p; c.lda = ldh; c.W = w.w_c; c.ldw = C; c.bias = w.b_c; c.out = x; c.ldo = C;
-    c.M = M; c.N = C; c.K = (w.attn ? 4 : 3) * C; c.epi = EPI_ACCUM_F32;
-    c.sel = 2; c.sel_span = C; c.sel_stride = C; c.plan = pl;
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
   if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
@@ -913,6 +930,7 @@ static int unet_forward_impl(ldmb_handle* h, const float* x_dev, float* out_dev,
                              const int32_t* t_index, int n_t, const float* const* te_host, const int32_t* plan,
                              const int32_t* plan_img, const ldmb_ddim_coef* coef, const float* noise_dev, void* stream) {
   if (!h || !x_dev || !out_dev || !t_index || (!plan && !plan_img)) return LDMB_ERR_INVALID;
+  CHECK_FAULT();
   const bool per_image = plan_img != nullptr;
   const bool pre = te_host == nullptr;      // FiLM tables of the n_t timesteps were precomputed (ldmb_unet_precompute_film)
   UNetState& u = h->unet;
@@ -1064,6 +1082,7 @@ extern "C" int ldmb_unet_forward_per_image(ldmb_handle* h, const float* x_dev, f
 
 extern "C" int ldmb_unet_precompute_film(ldmb_handle* h, int H, int W, int n_t, const float* const* te_host, void* stream) {
   if (!h || !te_host || n_t < 1) return LDMB_ERR_INVALID;
+  CHECK_FAULT();
   UNetState& u = h->unet;
   if (!u.configured) return fail(h, LDMB_ERR_STATE, "ldmb_unet_configure has not been called");
   if (!u.missing.empty())
@@ -1277,6 +1296,7 @@ extern "C" int ldmb_vae_reserve(ldmb_handle* h, int which, int max_batch, int H,
 extern "C" int ldmb_vae_decode(ldmb_handle* h, const float* z_dev, float* img_dev, uint8_t* img_u8_dev, int B, int hl,
                                int wl, void* stream) {
   if (!h || !z_dev || (!img_dev && !img_u8_dev)) return LDMB_ERR_INVALID;
+  CHECK_FAULT();
   VaeState& v = h->vae[LDMB_VAE_DECODER];
   if (!v.configured) return fail(h, LDMB_ERR_STATE, "decoder not configured");
   if (!v.missing.empty())
@@ -1319,6 +1339,7 @@ extern "C" int ldmb_vae_decode(ldmb_handle* h, const float* z_dev, float* img_de
 
 extern "C" int ldmb_vae_encode(ldmb_handle* h, const float* img_dev, float* z_dev, int B, int H, int W, void* stream) {
   if (!h || !img_dev || !z_dev) return LDMB_ERR_INVALID;
+  CHECK_FAULT();
   VaeState& v = h->vae[LDMB_VAE_ENCODER];
   if (!v.configured) return fail(h, LDMB_ERR_STATE, "encoder not configured");
   if (!v.missing.empty())

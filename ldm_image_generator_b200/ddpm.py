@@ -147,6 +147,8 @@ class DDPM(nn.Module):
                 bar.set_description(f"t: {t}, sigma: {sigma}")
             bar.update(1)
         bar.close()
+        if fused and self.model._handle is not None:
+            self.model._handle.raise_on_fault()     # watchdog word, polled without a stall: never hand back garbage silently
         return x
 
     @torch.no_grad()
@@ -194,5 +196,6 @@ class DDPM(nn.Module):
             x = self.model.denoise_step(x, t, co, e, check_params=(k == 0), plans_per_image=plans[:, k])
             bar.update(1)
         bar.close()
+        self.model._handle.raise_on_fault()
         return x
 

@@ -78,7 +78,11 @@ def encode_image_folder(source_dirs: Sequence[str], cache_dir: str, encoder: tor
             with Image.open(paths[done + k]) as im:
                 staging[k].copy_(torch.from_numpy(preprocess_image(im, size)))
         z = encoder(staging[:n].to(device, non_blocking=True))
-        for k in range(n):     # serialising a device tensor synchronises: the staging buffer is free again afterwards
+        torch.cuda.synchronize(device) if device.type == "cuda" else None     # the staging buffer is free again afterwards
+        handle = getattr(encoder, "_handle", None)
+        if handle is not None:
+            handle.raise_on_fault()        # never write latents of a faulted kernel into the cache
+        for k in range(n):
             torch.save(z[k:k + 1].clone(), os.path.join(cache_dir, f"{done + k}.pt"))
         done += n
     return done

@@ -97,7 +97,16 @@ class Handle:
         self.check(self.lib.ldmb_set_use_graphs(self.h, int(on)))
 
     def device_fault(self) -> int:
+        """The watchdog word, read on the device: synchronises the current stream."""
         return int(self.lib.ldmb_check_device_fault(self.h, stream_ptr(self.device)))
+
+    def raise_on_fault(self, synchronize: bool = False) -> None:
+        """Raise ``LdmbError`` if a tcgen05 pipeline watchdog has fired on this handle -- results produced since are
+        garbage.  Without ``synchronize`` the host-mapped mirror is polled (no stall; sees kernels that have run)."""
+        code = self.device_fault() if synchronize else int(self.lib.ldmb_poll_device_fault(self.h))
+        if code != 0:
+            raise LdmbError(f"libldmb200: kernel fault: a tcgen05 pipeline watchdog fired (code {code}); "
+                            "outputs computed on this handle since then are invalid")
 
     PROFILE_CLASSES = ("gemm_ffn_ab", "gemm_ffn_c", "gemm_qkv", "gemm_encodings", "gemm_level_change", "grouped_conv3x3",
                        "vae_conv3x3", "vae_gemm", "gemm_cuda_core", "channelnorm_film", "window_attention", "stem_final", "other")

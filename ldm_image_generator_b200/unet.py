@@ -113,6 +113,27 @@ class UNet(nn.Module):
             self._handle.set_deterministic(self._deterministic)
         return self
 
+    _RUNTIME_STATE = ("_handle", "_pe_res", "_film")
+
+    def __getstate__(self):
+        """copy.deepcopy / pickle / torch.save(module): the device handle (ctypes pointers) and the caches tied to it are
+        per-object runtime state, rebuilt on first use -- the reference module supports all three."""
+        state = self.__dict__.copy()
+        for k in self._RUNTIME_STATE:
+            state[k] = None
+        state.pop("_param_items", None)
+        state.pop("_te_cache", None)
+        return state
+
+    def invalidate_weights(self) -> None:
+        """Force a re-upload of every parameter (and a recomputation of the FiLM tables) at the next call.  Parameter
+        changes are detected by (storage, ``_version``, shape, dtype); writes THROUGH ``.data`` (``p.data.copy_()``, common
+        in EMA / weight-averaging code) do not bump ``_version`` -- call this after them."""
+        if self._handle is not None:
+            self._handle._param_keys.clear()
+        self._film = None
+        self.__dict__.pop("_param_items", None)
+
     def blocks_in_execution_order(self) -> List[SwinBlock]:
         out = []
         for st in list(self.encoder_stages) + list(self.decoder_stages):

@@ -51,6 +51,19 @@ class _VaeNet(nn.Module):
             self.precision, self._handle = precision, None
         return self
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle / torch.save(module): the device handle (ctypes pointers) is per-object state that is
+        rebuilt on first use -- the reference modules support all three."""
+        state = self.__dict__.copy()
+        state["_handle"] = None
+        return state
+
+    def invalidate_weights(self) -> None:
+        """Force a re-upload of every parameter at the next call.  Needed after writes THROUGH ``.data``
+        (``p.data.copy_()``, EMA code), which do not bump ``p._version`` and so are not detected."""
+        if self._handle is not None:
+            self._handle._param_keys.clear()
+
     def _prepare(self, device: torch.device) -> runtime.Handle:
         h = self._handle
         if h is None or h.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
@@ -89,6 +102,7 @@ class Encoder(_VaeNet):
             h = self._prepare(x.device)
             z = torch.empty(x.shape[0], self.latent_channels, x.shape[2] // f, x.shape[3] // f, device=x.device)
             h.vae_encode(x, z)
+            h.raise_on_fault()
         return z
 
 
@@ -122,6 +136,7 @@ class Decoder(_VaeNet):
             img = torch.empty(B, self.image_channels, hl * f, wl * f, device=z.device) if want_f32 else None
             u8 = torch.empty(B, hl * f, wl * f, self.image_channels, device=z.device, dtype=torch.uint8) if want_u8 else None
             h.vae_decode(z, img, u8)
+            h.raise_on_fault()
         return img, u8
 
     def forward(self, x):

@@ -123,3 +123,42 @@ def test_plan_replay_in_c_consumes_python_random_exactly():
             if mode != "mixed":
                 random.seed(seed); [random.random() for _ in range(seed)]
                 assert [tuple(p) for p in fast[-1].tolist()] == [R.draw_plan(nblk, mode == "train") for _ in range(n)][-1]
+
+
+def test_modules_deepcopy_and_pickle_without_a_handle():
+    """The reference modules can be deep-copied and torch.save'd; the ctypes handle is runtime state and is dropped."""
+    import copy
+    import io
+    from ldm_image_generator_b200 import Decoder, UNet
+    u = UNet(8, [1, 1], [64, 128])
+    u._handle, u._film = object(), (1, 2, 3)           # stand-ins for live runtime state
+    v = copy.deepcopy(u)
+    assert v._handle is None and v._film is None and u._handle is not None
+    buf = io.BytesIO()
+    u._handle = None
+    torch.save(u, buf)
+    d = copy.deepcopy(Decoder(channels=[64, 32], stages=[1, 1]))
+    assert d._handle is None
+    u.invalidate_weights(); d.invalidate_weights()      # no handle yet: no-ops
+
+
+def test_reference_staging_recipe_matches_the_reference():
+    """oracle/make_ref.py stages the unmodified reference byte for byte (build container only)."""
+    import hashlib
+    import json
+    import os
+    import sys
+    if not os.path.isfile("/root/reference/unet.py"):
+        pytest.skip("/root/reference not present on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    try:
+        import make_ref
+    finally:
+        sys.path.pop(0)
+    d = make_ref.stage()
+    man = json.load(open(os.path.join(d, "MANIFEST.json")))["files"]
+    assert set(make_ref.FILES) == set(man)
+    for f, digest in man.items():
+        assert hashlib.sha256(open(os.path.join("/root/reference", f), "rb").read()).hexdigest() == digest
+    assert make_ref.available() == d

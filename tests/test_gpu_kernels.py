@@ -152,6 +152,31 @@ def test_window_attention_mma_kernel(handles, B, H, W, C, wh, ww, shift):
     assert h.device_fault() == 0
 
 
+@pytest.mark.parametrize("B,H,W,C,shift", [(2, 12, 12, 128, 0), (2, 12, 12, 128, 3), (2, 20, 28, 256, 3), (2, 20, 28, 256, 0),
+                                           (2, 8, 8, 512, 3), (2, 8, 8, 512, 0), (1, 32, 32, 128, 3), (1, 32, 32, 128, 0),
+                                           (3, 4, 4, 1024, 0), (2, 16, 16, 256, 3), (1, 10, 7, 128, 3)])
+def test_window_attention_core_vs_oracle(handles, B, H, W, C, shift):
+    """The attention core against oracle.restate.window_attention DIRECTLY (attention.py:13-85 + torch MHA), shifted and
+    zero-padded windows included: in-projection done in torch (the kernel's input is qkv), out-projection = identity."""
+    from oracle import restate as R
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + H * 7 + W + C + shift)
+    xm = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w_in = (torch.randn(3 * C, C, device="cuda", generator=g) / C ** 0.5).bfloat16().float()
+    b_in = torch.randn(3 * C, device="cuda", generator=g) * 0.5
+    qkv = (xm.float().reshape(-1, C) @ w_in.t() + b_in).reshape(B, H, W, 3 * C).bfloat16()
+    out = torch.full((B, H, W, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    glob = H <= 6 and W <= 6
+    h.window_attention(qkv, xm, b_in, out, B, H, W, C, H if glob else 6, W if glob else 6, 0 if glob else shift)
+    sd = {"a.attention.in_proj_weight": w_in.cpu(), "a.attention.in_proj_bias": b_in.cpu(),
+          "a.attention.out_proj.weight": torch.eye(C), "a.attention.out_proj.bias": torch.zeros(C)}
+    want = R.window_attention(sd, "a.", xm.float().cpu().permute(0, 3, 1, 2).contiguous(), shift).permute(0, 2, 3, 1)
+    err = _rel(out.float().cpu(), want)
+    print("window attention vs oracle", (B, H, W, C, shift), err)
+    assert err < 8e-3          # qkv and the output are rounded to bf16 on the kernel side only
+    assert h.device_fault() == 0
+
+
 def _pack_grouped(w):
     """[C, 32, 3, 3] grouped-conv weight -> block-diagonal pairs [C/64][64][9*64] (ldmb.h: ldmb_grouped_conv3x3)."""
     C = w.shape[0]
