@@ -226,7 +226,8 @@ int ldmb_channelnorm_film(ldmb_handle* h, const float* x, const float* film, voi
 /* Window attention core (attention.py:13-85 + torch MHA, after in_proj and before out_proj): qkv [B*H*W, 3C] and
  * xm [B*H*W, C] in the handle's precision, b_in fp32 [3C] (in_proj bias: the q/k/v of zero-padded tokens),
  * att [B*H*W, ldo>=C].  window win_h x win_w, shift 0 (bool pad mask) or != 0 (rolled window, float key bias =
- * channel 0 of the rolled xm).  force_simt: the CUDA-core kernel instead of the mma.sync one in bf16 mode. */
+ * channel 0 of the rolled xm).  force_simt: 0 = the tcgen05 kernel (bf16 mode; falls back to mma.sync / CUDA cores for shapes it does not
+ * cover), 1 = the CUDA-core kernel, 2 = the mma.sync kernel. */
 int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const float* b_in, void* att, int64_t ldo,
                           int B, int H, int W, int C, int win_h, int win_w, int shift, int force_simt, void* stream);
 

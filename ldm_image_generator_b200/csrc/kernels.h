@@ -74,6 +74,12 @@ bool window_attention_mma_supported(int C, int head_dim, int win_h, int win_w, l
 cudaError_t launch_window_attention_mma(const void* qkv, const void* xm, const float* b_in, void* att, long long ldo, int B,
                                         int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
                                         cudaStream_t st);
+// tcgen05 implementation of the same contract (kernels_attn_tc.cu): S = q k^T and O = P v as UMMA tiles over 128-row tiles
+// that pack several windows, softmax from TMEM; two heads (64 channels) per work item
+bool window_attention_tc_supported(int B, int H, int W, int C, int head_dim, int win_h, int win_w, long long ldo);
+cudaError_t launch_window_attention_tc(TcContext* ctx, const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
+                                       int B, int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
+                                       cudaStream_t st);
 // decoder_last ConvTranspose (unet.py:78,102) fused with the DDIM update (ddpm.py:81-91).
 // x fp32 [B*H*W, C0]; w fp32 [C0][Cin*s*s]; x_in/out/noise NCHW fp32 [B,Cin,H*s,W*s]; ddim_enabled 0 = eps only.
 // sp (device): x_in / out / noise pointers and the DDIM scalars of this step.

@@ -1,0 +1,386 @@
+// Window attention core on tcgen05 / TMEM (sm_100a): S = q k^T and O = P v as UMMA tiles, fp32 softmax from TMEM.
+//
+// attention.py:13-85 + torch MHA as called there (attention.py:82): per (image, window, head)
+//   S = (q / sqrt(32)) k^T + key bias,  P = softmax_keys(S),  O = P v.
+// A window has L <= 36 tokens and a head 32 channels, so one (window, head) problem is far below a 128-row UMMA tile.
+// Instead of one problem per tile, a tile packs 128 / SLOT windows, each in a SLOT-row slot (SLOT = 64 for the 6x6
+// windows, 32 when L <= 32), and ONE M128 x N128 x K32 UMMA computes every query x key product of the tile; the
+// softmax only reads its own window's diagonal block of the accumulator, and P is written into a [128 x 128] bf16
+// operand that is zero outside the diagonal blocks, so O = P v (M128 x N32 x K128) never mixes windows.  The wasted
+// off-diagonal MACs are free (the kernel is bound by moving q/k/v and by the softmax, not by the tensor pipe).
+//
+// Work item = (tile, pair of heads) = 64 channels = 128-byte rows.  Warp roles (13 warps):
+//   warps 0-7   softmax / epilogue: two groups of 4 warps (TMEM lane quadrant = warp % 4), group g owns head g of the
+//               pair: tcgen05.ld of its window's S block -> scale, key bias, row softmax in fp32 -> P (bf16, 128B-swizzled
+//               smem) -> later O from TMEM, normalised, 64-byte store per token (pad tokens are cropped, attention.py:56)
+//   warps 8-11  loaders: thread = tile row = one token; the pad / roll / window-split copies of the reference
+//               (attention.py:27-50) are index arithmetic here; q | k | v rows gathered with 16-byte cp.async into
+//               128B-swizzled K-major panels (3 stages); pad tokens: k = v = 0 (shift == 0, masked by the -inf key bias) or
+//               the in-projection bias (shift != 0: x = 0 there, and the float "mask" keeps those keys live)
+//   warp 12     MMA issuer (whole warp runs the loop, one elected lane issues): S for item j, then P v for item j - 1
+// V is the B operand of P v in MN-major form ([key][d] rows as loaded, no transpose): instruction descriptor bit 16.
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tc_context.h"
+
+namespace {
+
+constexpr int kD = 32;                       // head_dim (unet.py:26)
+constexpr int kStages = 3;
+constexpr int kPanel = 128 * 128;            // [128 rows x 64 bf16] = 16 KB, 128-byte rows
+constexpr int kStageBytes = 3 * kPanel;      // q | k | v panels of one item
+constexpr int kPBytes = 2 * kPanel;          // P [128 x 128 keys] bf16 = two K-panels
+constexpr int kSoftWarps = 8, kLoadWarps = 4;
+constexpr int kMmaWarp = kSoftWarps + kLoadWarps;
+constexpr int kThreads = 32 * (kMmaWarp + 1);
+constexpr int kMetaBytes = kStages * 128 * 8;
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kPBytes + kMetaBytes + 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnGeom {
+  int B, H, W, C, wh, ww, shift, Hp, Wp;
+  int L, wpt;                 // tokens per window, windows per 128-row tile
+  int nww, nwin, n_windows, n_pairs, n_items;
+  long long ldo;
+};
+
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    if (*s_abort) return false;
+    if (clock64() - t0 > 3000000000LL) {
+      *s_abort = 1;
+      report_fault(fault, code);
+      return false;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// SLOT = rows of a tile reserved per window: 64 (32 < L <= 36) or 32 (L <= 32)
+template <int SLOT>
+__global__ void __launch_bounds__(kThreads, 1)
+window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ xm, const float* __restrict__ b_in,
+                           bf16* __restrict__ att, const AttnGeom g, const int* __restrict__ skip, int* fault) {
+  constexpr int NV = SLOT == 64 ? 36 : 32;            // accumulator columns a softmax thread reads (>= L)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* pbuf = stages + kStages * kStageBytes;
+  float* meta_kb = reinterpret_cast<float*>(pbuf + 2 * kPBytes);     // [stage][128] key bias * log2(e)
+  int* meta_m = reinterpret_cast<int*>(meta_kb + kStages * 128);     // [stage][128] token index of the row, -1: not a stored query
+  uint64_t* full = reinterpret_cast<uint64_t*>(meta_m + kStages * 128);
+  uint64_t* empty = full + kStages;
+  uint64_t* s_full = empty + kStages;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* pv_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full[i], 32 * kLoadWarps); ptx::mbar_init(&empty[i], 1 + kSoftWarps); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 4);
+      ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&pv_done[i], 1);
+    }
+    *s_abort = 0;
+    ptx::fence_barrier_init();
+  }
+  if (warp == kMmaWarp) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  // Zero every operand buffer once: rows no loader ever writes (slot rows >= L) and P outside the diagonal blocks must
+  // read as 0 -- a NaN bit pattern there would reach every output through 0 * NaN.
+  for (int i = threadIdx.x; i < (kStages * kStageBytes + 2 * kPBytes) / 16; i += kThreads)
+    ptx::st_shared_v4(ptx::smem_u32(stages) + i * 16, 0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const bool skipped = skip != nullptr && *skip != 0;              // stochastic depth (unet.py:39-40)
+  const int n_items = skipped ? 0 : g.n_items;
+  const int n_my = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp >= kSoftWarps && warp < kMmaWarp) {
+    // ===================================================== loaders: thread = tile row = token
+    const int t = threadIdx.x - 32 * kSoftWarps;
+    const int w = t / SLOT, sl = t % SLOT;
+    const uint32_t sw = static_cast<uint32_t>(t & 7);
+    int cur_tile = -1;
+    bool live = false, fill = false, bias_fill = false;     // live: real token; fill: k / v of this row must be written finite
+    long long m = 0;
+    float kbv = 0.f;
+    int issued = 0, prev_s = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = item / g.n_pairs, pair = item % g.n_pairs;
+      const int s = it % kStages;
+      if (tile != cur_tile) {
+        cur_tile = tile;
+        const int gw = tile * g.wpt + w;                    // window index over the batch
+        live = false; fill = false; bias_fill = false; kbv = 0.f; m = 0;
+        if (sl < g.L) {
+          fill = true;
+          if (gw < g.n_windows) {
+            const int b = gw / g.nwin, win = gw % g.nwin, wi = win / g.nww, wj = win % g.nww;
+            const int si = sl / g.ww, sj = sl % g.ww;
+            // position in the zero-padded frame of the token that the roll (attention.py:39) brings to this window slot
+            const int pi = (wi * g.wh + si - g.shift + g.Hp) % g.Hp, pj = (wj * g.ww + sj - g.shift + g.Wp) % g.Wp;
+            const bool pad = pi >= g.H || pj >= g.W;
+            live = !pad;
+            m = ((long long)b * g.H + pi) * g.W + pj;
+            if (g.shift == 0) {
+              kbv = pad ? -INFINITY : 0.f;                  // bool key_padding_mask (attention.py:27-35)
+            } else {                                        // float "mask" = rolled activation, channel 0 (attention.py:40)
+              const int qi = (pi - g.shift + g.Hp) % g.Hp, qj = (pj - g.shift + g.Wp) % g.Wp;
+              kbv = (qi < g.H && qj < g.W) ? __bfloat162float(xm[(((long long)b * g.H + qi) * g.W + qj) * g.C]) * kLog2e : 0.f;
+              bias_fill = pad;                              // x = 0 there: k, v = in-projection bias, and the key stays live
+            }
+          } else {
+            kbv = -INFINITY;
+          }
+        }
+      }
+      if (!wait_bar(&empty[s], ((it / kStages) & 1) ^ 1, s_abort, fault, 41)) break;
+      meta_kb[s * 128 + t] = kbv;
+      meta_m[s * 128 + t] = live ? (int)m : -1;
+      const uint32_t row = ptx::smem_u32(stages + s * kStageBytes) + t * 128;
+      if (live) {
+        const bf16* src = qkv + m * 3 * g.C + pair * 64;
+#pragma unroll
+        for (int which = 0; which < 3; ++which)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::cp_async_16(row + which * kPanel + ((c ^ sw) << 4), src + (long long)which * g.C + c * 8);
+      } else if (fill) {
+#pragma unroll
+        for (int which = 1; which < 3; ++which) {
+          const float* bp = b_in + (long long)which * g.C + pair * 64;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v0 = 0u, v1 = 0u, v2 = 0u, v3 = 0u;
+            if (bias_fill) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(bp + c * 8)), b4 = __ldg(reinterpret_cast<const float4*>(bp + c * 8 + 4));
+              v0 = pack_bf16(a.x, a.y); v1 = pack_bf16(a.z, a.w); v2 = pack_bf16(b4.x, b4.y); v3 = pack_bf16(b4.z, b4.w);
+            }
+            ptx::st_shared_v4(row + which * kPanel + ((c ^ sw) << 4), v0, v1, v2, v3);
+          }
+        }
+      }
+      ptx::cp_async_commit();
+      if (issued > 0) {          // the previous item's copies have landed: publish it (its loads overlapped this item's issue)
+        ptx::cp_async_wait<1>();
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&full[prev_s]);
+      }
+      prev_s = s;
+      ++issued;
+    }
+    if (issued > 0) {
+      ptx::cp_async_wait<0>();
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full[prev_s]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================================== MMA issuer
+    const bool issuer = ptx::elect_one();
+    constexpr uint32_t idesc_s = ptx::idesc_bf16(128, 128);
+    constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, kD) | (1u << 16);      // B (= v) MN-major: rows = keys, 32 d contiguous
+    bool ok = true;
+    for (int j = 0; ok && j <= n_my; ++j) {
+      if (j < n_my) {           // S = q k^T of item j, both heads
+        const int s = j % kStages;
+        if (!wait_bar(&full[s], (j / kStages) & 1, s_abort, fault, 42)) break;
+        ptx::tc_fence_after();
+        const uint64_t q_desc = ptx::smem_desc_sw128(ptx::smem_u32(stages + s * kStageBytes));
+        const uint64_t k_desc = q_desc + kPanel / 16;
+        for (int h = 0; h < 2; ++h) {
+          if (!wait_bar(&s_empty[h], (j & 1) ^ 1, s_abort, fault, 43)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (issuer) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)      // head h = bytes [64 h, 64 h + 64) of the 128-byte rows, K = 32 = 2 x 16
+              ptx::umma_f16(tmem_base + h * 128, q_desc + 4 * h + 2 * k, k_desc + 4 * h + 2 * k, idesc_s, k);
+            ptx::umma_commit(&s_full[h]);
+          }
+          __syncwarp();
+        }
+        if (!ok) break;
+      }
+      if (j >= 1) {             // O = P v of item j - 1
+        const int i = j - 1, s = i % kStages;
+        const uint64_t v_desc = ptx::smem_desc_sw128(ptx::smem_u32(stages + s * kStageBytes + 2 * kPanel));
+        for (int h = 0; h < 2; ++h) {
+          if (!wait_bar(&p_full[h], i & 1, s_abort, fault, 44)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (issuer) {
+            const uint64_t p_desc = ptx::smem_desc_sw128(ptx::smem_u32(pbuf + h * kPBytes));
+            uint32_t acc = 0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {           // 16 keys per step
+              if ((kk * 16) % SLOT >= g.L) continue;   // keys of this step all lie beyond the windows' L tokens: P is 0 there
+              ptx::umma_f16(tmem_base + 256 + h * kD, p_desc + (kk / 4) * (kPanel / 16) + (kk % 4) * 2,
+                            v_desc + kk * (16 * 128 / 16) + 4 * h, idesc_pv, acc);
+              acc = 1;
+            }
+            ptx::umma_commit(&pv_done[h]);
+          }
+          __syncwarp();
+        }
+        if (!ok) break;
+        if (issuer) ptx::umma_commit(&empty[s]);       // q, k, v of the stage are consumed once these MMAs complete
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== softmax / epilogue: group = head of the pair
+    const int grp = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const int w = row / SLOT;                                   // warp-uniform (SLOT is a multiple of 32)
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const float scale_l2 = 0.17677669529663687f * kLog2e;       // 1/sqrt(32) * log2(e)
+    // P row of this thread: key columns [w SLOT, w SLOT + L) -> K-panel (w SLOT) / 64, 16-byte chunks from ((w SLOT) % 64) / 8
+    const uint32_t p_row = ptx::smem_u32(pbuf + grp * kPBytes) + ((w * SLOT) / 64) * kPanel + row * 128;
+    const int chunk0 = ((w * SLOT) % 64) / 8;
+    int m_prev = -1;
+    float inv_prev = 0.f;
+    bool ok = true;
+    auto epilogue = [&](int i) -> bool {                        // O of item i (this group's head) -> att
+      if (!wait_bar(&pv_done[grp], i & 1, s_abort, fault, 45)) return false;
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(tmem_base + lane_off + 256 + grp * kD, o);
+      ptx::tmem_ld_wait();
+      if (m_prev >= 0) {
+        const int pair = ((int)blockIdx.x + i * (int)gridDim.x) % g.n_pairs;
+        uint4* dst = reinterpret_cast<uint4*>(att + (long long)m_prev * g.ldo + pair * 64 + grp * kD);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          dst[u] = make_uint4(pack_bf16(__uint_as_float(o[8 * u]) * inv_prev, __uint_as_float(o[8 * u + 1]) * inv_prev),
+                              pack_bf16(__uint_as_float(o[8 * u + 2]) * inv_prev, __uint_as_float(o[8 * u + 3]) * inv_prev),
+                              pack_bf16(__uint_as_float(o[8 * u + 4]) * inv_prev, __uint_as_float(o[8 * u + 5]) * inv_prev),
+                              pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_prev, __uint_as_float(o[8 * u + 7]) * inv_prev));
+      }
+      return true;
+    };
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % kStages;
+      if (!wait_bar(&full[s], (it / kStages) & 1, s_abort, fault, 46)) { ok = false; break; }
+      const int m_cur = meta_m[s * 128 + row];
+      if (!wait_bar(&s_full[grp], it & 1, s_abort, fault, 47)) { ok = false; break; }
+      ptx::tc_fence_after();
+      float v[NV];
+      {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_off + grp * 128 + w * SLOT, r);
+        if (SLOT == 64) {
+          uint32_t r4[4];
+          ptx::tmem_ld_32x4(tmem_base + lane_off + grp * 128 + w * SLOT + 32, r4);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[(32 + i) % NV] = __uint_as_float(r4[i]);
+        } else {
+          ptx::tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[grp]);           // the next item's S may overwrite the accumulator
+      // ---- softmax over the window's keys (fp32, exp2 domain)
+      const float* kbp = meta_kb + s * 128 + w * SLOT;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        v[i] = i < g.L ? fmaf(v[i], scale_l2, kbp[i]) : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      if (mx == -INFINITY) mx = 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { v[i] = exp2f(v[i] - mx); sum += v[i]; }
+      const float inv = 1.f / sum;
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty[s]);               // this stage's metadata has been read
+      // ---- previous item of this head: P v has completed (P buffer free), its O leaves through this warp
+      if (it > 0 && !epilogue(it - 1)) { ok = false; break; }
+      if (m_cur >= 0) {
+#pragma unroll
+        for (int c = 0; c < (NV + 7) / 8; ++c) {
+          if (c * 8 >= g.L) break;
+          float e[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) e[u] = (c * 8 + u < NV) ? v[(c * 8 + u) % NV] : 0.f;    // keys >= L: exp2(-inf) = 0 already
+          ptx::st_shared_v4(p_row + (((chunk0 + c) ^ sw) << 4), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
+                            pack_bf16(e[6], e[7]));
+        }
+      }
+      ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      ptx::tc_fence_before();            // orders the O read above before the MMA that overwrites the accumulator
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
+      m_prev = m_cur;
+      inv_prev = inv;
+    }
+    if (ok && n_my > 0) epilogue(n_my - 1);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+static const bool g_attn_tc = getenv("LDMB_ATTN_TC") == nullptr || atoi(getenv("LDMB_ATTN_TC")) != 0;   // debug: 0 = mma.sync kernel
+
+bool window_attention_tc_supported(int B, int H, int W, int C, int head_dim, int win_h, int win_w, long long ldo) {
+  const long long tokens = (long long)B * H * W;
+  return g_attn_tc && head_dim == kD && C % 64 == 0 && win_h * win_w <= 36 && win_h >= 1 && win_w >= 1 && ldo % 8 == 0 &&
+         tokens < (1LL << 31);
+}
+
+cudaError_t launch_window_attention_tc(TcContext* ctx, const void* qkv, const void* xm, const float* b_in, void* att, long long ldo,
+                                       int B, int H, int W, int C, int win_h, int win_w, int shift, const int* skip,
+                                       cudaStream_t st) {
+  if (!window_attention_tc_supported(B, H, W, C, kD, win_h, win_w, ldo)) return cudaErrorNotSupported;
+  AttnGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.H = H; g.W = W; g.C = C; g.wh = win_h; g.ww = win_w; g.shift = shift; g.ldo = ldo;
+  g.Hp = (H + win_h - 1) / win_h * win_h; g.Wp = (W + win_w - 1) / win_w * win_w;
+  g.L = win_h * win_w;
+  const int slot = g.L <= 32 ? 32 : 64;
+  g.wpt = 128 / slot;
+  g.nww = g.Wp / win_w; g.nwin = (g.Hp / win_h) * g.nww;
+  const long long n_windows = (long long)B * g.nwin;
+  const long long n_tiles = (n_windows + g.wpt - 1) / g.wpt;
+  g.n_pairs = C / 64;
+  if (n_windows >= (1LL << 31) || n_tiles * g.n_pairs >= (1LL << 31)) return cudaErrorNotSupported;
+  g.n_windows = (int)n_windows;
+  g.n_items = (int)(n_tiles * g.n_pairs);
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr.mark(ctx->device);
+  }
+  const int grid = g.n_items < ctx->num_sms ? g.n_items : ctx->num_sms;
+  const bf16* q = static_cast<const bf16*>(qkv);
+  const bf16* x = static_cast<const bf16*>(xm);
+  bf16* o = static_cast<bf16*>(att);
+  if (slot == 64) return launch_k((window_attention_tc_kernel<64>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev);
+  return launch_k((window_attention_tc_kernel<32>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev);
+}

@@ -223,6 +223,20 @@ GemmDesc gd() {
   return d;
 }
 
+// Window attention core (attention.py:13-85 + torch MHA): tcgen05 kernel where the shape allows, else the mma.sync / CUDA-core ones.
+// mode: 0 default, 1 CUDA-core kernel, 2 mma.sync kernel (tests compare the three)
+int window_attention(ldmb_handle* h, const void* qkv, const void* xm, const float* b_in, void* att, long long ldo, int B, int Hl, int Wl,
+                     int C, int wh, int ww, int shift, const int* pl, cudaStream_t st, int mode) {
+  const double bytes = (double)B * Hl * Wl * C * 4 * h->tsize();
+  if (h->bf16() && !h->force_simt && mode == 0 && window_attention_tc_supported(B, Hl, Wl, C, kHeadDim, wh, ww, ldo)) {
+    CKLP(PK_ATTN, bytes, launch_window_attention_tc(h->tc, qkv, xm, b_in, att, ldo, B, Hl, Wl, C, wh, ww, shift, pl, st));
+    return LDMB_OK;
+  }
+  CKLP(PK_ATTN, bytes, launch_window_attention(qkv, xm, b_in, att, ldo, h->bf16(), B, Hl, Wl, C, kHeadDim, wh, ww, shift, pl, st,
+                                               mode == 1 || h->force_simt));
+  return LDMB_OK;
+}
+
 // x fp32 [B,H,W,C] += grouped conv3x3(xm) + bias (unet.py:30: groups of 32 channels).
 // tcgen05, halo-patch kernel (every activation read once) when C % 64 == 0, else the generic implicit-GEMM path.
 int grouped_conv(ldmb_handle* h, const void* xm, const void* w_g, const float* b_g, float* x, int B, int Hl, int Wl, int C,
@@ -707,9 +721,8 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE; d.plan = pl;
     if ((rc = gemm(h, d, st, PK_QKV))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
-    CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
-         launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
-                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, pl, st));
+    if ((rc = window_attention(h, u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, B, Hl, Wl, C, global ? Hl : kWindow,
+                               global ? Wl : kWindow, global ? 0 : w.shift, pl, st, 0))) return rc;
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
   if (fused_ffn) {
@@ -770,9 +783,8 @@ int run_block_per_image(ldmb_handle* h, const BlockW& w, int block_index, int B,
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE;
     if ((rc = gemm(h, d, st, PK_QKV))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;
-    CKLP(PK_ATTN, (double)M * C * 4 * h->tsize(),
-         launch_window_attention(u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 5LL * C), ldh, h->bf16(), B, Hl, Wl, C, kHeadDim,
-                                 global ? Hl : kWindow, global ? Wl : kWindow, global ? 0 : w.shift, nullptr, st));
+    if ((rc = window_attention(h, u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 5LL * C), ldh, B, Hl, Wl, C, global ? Hl : kWindow,
+                               global ? Wl : kWindow, global ? 0 : w.shift, nullptr, st, 0))) return rc;
   }
   if (fused) {
     CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
@@ -1422,10 +1434,7 @@ extern "C" int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void
     return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CKLP(PK_ATTN, (double)B * H * W * C * 4 * h->tsize(),
-       launch_window_attention(qkv, xm, b_in, att, ldo, h->bf16(), B, H, W, C, kHeadDim, win_h, win_w, shift, nullptr, st,
-                               force_simt != 0));
-  return LDMB_OK;
+  return window_attention(h, qkv, xm, b_in, att, ldo, B, H, W, C, win_h, win_w, shift, nullptr, st, force_simt);
 }
 
 extern "C" int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* w_packed, const float* bias, float* x, int B,

@@ -235,7 +235,7 @@ class Handle:
 
     def window_attention(self, qkv, xm, b_in, att, B, H, W, Cc, win_h, win_w, shift, force_simt=False) -> None:
         self.check(self.lib.ldmb_window_attention(self.h, qkv.data_ptr(), xm.data_ptr(), b_in.data_ptr(), att.data_ptr(),
-                                                  att.stride(-2), B, H, W, Cc, win_h, win_w, shift, int(force_simt),
+                                                  att.stride(-2), B, H, W, Cc, win_h, win_w, shift, int(force_simt),   # 0 tcgen05, 1 CUDA cores, 2 mma.sync
                                                   stream_ptr(self.device)))
 
     def channelnorm_film(self, x, film, out, M, Cc, HW) -> None:

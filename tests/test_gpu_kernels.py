@@ -129,9 +129,10 @@ def _window_attention_torch(qkv, C, ws):
 
 @pytest.mark.parametrize("B,H,W,C,wh,ww,shift", [(2, 12, 12, 128, 6, 6, 0), (2, 12, 12, 128, 6, 6, 3), (3, 20, 28, 256, 6, 6, 0),
                                                  (3, 20, 28, 256, 6, 6, 3), (5, 4, 4, 1024, 4, 4, 0), (2, 8, 8, 512, 6, 6, 3),
-                                                 (1, 32, 32, 128, 6, 6, 3), (2, 5, 3, 128, 5, 3, 0)])
+                                                 (1, 32, 32, 128, 6, 6, 3), (2, 5, 3, 128, 5, 3, 0), (64, 32, 32, 128, 6, 6, 3),
+                                                 (64, 16, 16, 256, 6, 6, 0), (64, 4, 4, 1024, 4, 4, 0), (7, 6, 6, 64, 6, 6, 0)])
 def test_window_attention_mma_kernel(handles, B, H, W, C, wh, ww, shift):
-    """bf16 mma.sync attention core vs the CUDA-core kernel (validated against the reference through the UNet
+    """tcgen05 (and mma.sync) attention core vs the CUDA-core kernel (validated against the reference through the UNet
     fixtures), including zero-padded windows, the rolled float key bias and the global small-image case."""
     h = handles["bf16"]
     g = torch.Generator(device="cuda").manual_seed(B * 131 + H * 17 + C + shift)
@@ -141,10 +142,13 @@ def test_window_attention_mma_kernel(handles, B, H, W, C, wh, ww, shift):
     ldo = 4 * C
     out = torch.full((B, H, W, ldo), 7.0, device="cuda", dtype=torch.bfloat16)
     ref = torch.full((B, H, W, ldo), 7.0, device="cuda", dtype=torch.bfloat16)
-    h.window_attention(qkv, xm, b_in, out[..., 3 * C:], B, H, W, C, wh, ww, shift)
-    h.window_attention(qkv, xm, b_in, ref[..., 3 * C:], B, H, W, C, wh, ww, shift, force_simt=True)
+    h.window_attention(qkv, xm, b_in, out[..., 3 * C:], B, H, W, C, wh, ww, shift)                       # tcgen05 kernel
+    h.window_attention(qkv, xm, b_in, ref[..., 3 * C:], B, H, W, C, wh, ww, shift, force_simt=1)         # CUDA-core kernel
     assert torch.equal(out[..., :3 * C], ref[..., :3 * C])          # nothing outside the output columns is touched
     assert _rel(out[..., 3 * C:].float(), ref[..., 3 * C:].float()) < 6e-3
+    mma = torch.full((B, H, W, ldo), 7.0, device="cuda", dtype=torch.bfloat16)
+    h.window_attention(qkv, xm, b_in, mma[..., 3 * C:], B, H, W, C, wh, ww, shift, force_simt=2)         # mma.sync kernel
+    assert _rel(mma[..., 3 * C:].float(), ref[..., 3 * C:].float()) < 6e-3
     if shift == 0 and H % wh == 0 and W % ww == 0:
         want = _window_attention_torch(qkv, C, wh) if wh == ww else None
         if want is not None:
