@@ -44,8 +44,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct AttnGeom {
   int B, H, W, C, wh, ww, shift, Hp, Wp;
   int L, wpt;                 // tokens per window, windows per 128-row tile
-  int nww, nwin, n_windows, n_pairs, n_items;
+  int nww, nwin, n_windows, n_pairs;
+  int n_units, ppu, n_groups;     // work units = tiles x n_groups, each ppu = n_pairs / n_groups consecutive head pairs
   long long ldo;
+  int dbg;   // debug experiments: 1 no softmax arithmetic, 2 no P v MMAs, 4 no S MMAs, 8 no q/k/v copies, 16 no output stores, 32 no P writes
 };
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* fault, int code) {
@@ -62,6 +64,12 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatil
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {     // 2^x, one MUFU op; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -71,7 +79,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int SLOT>
 __global__ void __launch_bounds__(kThreads, 1)
 window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ xm, const float* __restrict__ b_in,
-                           bf16* __restrict__ att, const AttnGeom g, const int* __restrict__ skip, int* fault) {
+                           bf16* __restrict__ att, const AttnGeom g, const int* __restrict__ skip, int* fault, long long* trace) {
   constexpr int NV = SLOT == 64 ? 36 : 32;            // accumulator columns a softmax thread reads (>= L)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,9 +95,13 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // debug (ldmb_debug_tc_trace): cycles one lane of each role spends per phase, 16 slots per CTA
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+  auto lap = [&](int slot) { if (trace != nullptr) { const long long now = clock64(); tacc[slot] += now - tlast; tlast = now; } };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full[i], 32 * kLoadWarps); ptx::mbar_init(&empty[i], 1 + kSoftWarps); }
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full[i], 2 * 32 * kLoadWarps); ptx::mbar_init(&empty[i], 1 + kSoftWarps); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 4);
       ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&pv_done[i], 1);
@@ -109,89 +121,111 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   const bool skipped = skip != nullptr && *skip != 0;              // stochastic depth (unet.py:39-40)
-  const int n_items = skipped ? 0 : g.n_items;
-  const int n_my = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // work unit = (tile, group of ppu head pairs): the tile's index arithmetic is shared by the unit's ppu items
+  const int n_units = skipped ? 0 : g.n_units;
+  const int n_units_my = (int)blockIdx.x < n_units ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_my = n_units_my * g.ppu;
 
   if (warp >= kSoftWarps && warp < kMmaWarp) {
-    // ===================================================== loaders: thread = tile row = token
+    // ===================================================== loaders
+    // Two thread mappings: (1) thread = tile row = token for the per-tile index arithmetic (published in meta_m / meta_kb),
+    // (2) thread = 16-byte chunk c of rows r0 + 16 i for the copies, so that a warp instruction moves 4 whole 128-byte rows.
     const int t = threadIdx.x - 32 * kSoftWarps;
     const int w = t / SLOT, sl = t % SLOT;
-    const uint32_t sw = static_cast<uint32_t>(t & 7);
-    int cur_tile = -1;
-    bool live = false, fill = false, bias_fill = false;     // live: real token; fill: k / v of this row must be written finite
-    long long m = 0;
+    const int si = sl / g.ww, sj = sl % g.ww;
+    const int c = t & 7, r0 = t >> 3;
+    const uint32_t dst_off = static_cast<uint32_t>(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 16 i) & 7 == r0 & 7
+    // row state of the unit's tile: code >= 0 token index (q, k, v copied); -1: k, v zero-filled; -2: k, v = in-projection bias;
+    // -3: slot row beyond the window's L tokens (stays zero)
+    int code = -3;
     float kbv = 0.f;
-    int issued = 0, prev_s = 0;
-    for (int it = 0; it < n_my; ++it) {
-      const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int tile = item / g.n_pairs, pair = item % g.n_pairs;
-      const int s = it % kStages;
-      if (tile != cur_tile) {
-        cur_tile = tile;
-        const int gw = tile * g.wpt + w;                    // window index over the batch
-        live = false; fill = false; bias_fill = false; kbv = 0.f; m = 0;
-        if (sl < g.L) {
-          fill = true;
-          if (gw < g.n_windows) {
-            const int b = gw / g.nwin, win = gw % g.nwin, wi = win / g.nww, wj = win % g.nww;
-            const int si = sl / g.ww, sj = sl % g.ww;
-            // position in the zero-padded frame of the token that the roll (attention.py:39) brings to this window slot
-            const int pi = (wi * g.wh + si - g.shift + g.Hp) % g.Hp, pj = (wj * g.ww + sj - g.shift + g.Wp) % g.Wp;
-            const bool pad = pi >= g.H || pj >= g.W;
-            live = !pad;
-            m = ((long long)b * g.H + pi) * g.W + pj;
-            if (g.shift == 0) {
-              kbv = pad ? -INFINITY : 0.f;                  // bool key_padding_mask (attention.py:27-35)
-            } else {                                        // float "mask" = rolled activation, channel 0 (attention.py:40)
-              const int qi = (pi - g.shift + g.Hp) % g.Hp, qj = (pj - g.shift + g.Wp) % g.Wp;
-              kbv = (qi < g.H && qj < g.W) ? __bfloat162float(xm[(((long long)b * g.H + qi) * g.W + qj) * g.C]) * kLog2e : 0.f;
-              bias_fill = pad;                              // x = 0 there: k, v = in-projection bias, and the key stays live
+    // The key bias of a shifted window is a gather from xm (one dependent global load per row and tile).  Issued right after a
+    // burst of cp.async it would queue behind them in the SM's load/store unit, so it is requested one unit AHEAD (kb_next),
+    // before the current unit's copies, and only converted when that unit starts.
+    int code_next = -3;
+    float kbv_next = 0.f;
+    bf16 kb_raw_next = __float2bfloat16_rn(0.f);
+    bool kb_from_xm_next = false;
+    auto tile_meta_issue = [&](int tile) {
+      const int gw = tile * g.wpt + w;                      // window index over the batch
+      code_next = -3; kbv_next = 0.f; kb_from_xm_next = false;
+      if (sl >= g.L) return;
+      code_next = -1; kbv_next = -INFINITY;
+      if (gw >= g.n_windows) return;
+      const int b = gw / g.nwin, win = gw - b * g.nwin, wi = win / g.nww, wj = win - wi * g.nww;
+      // position in the zero-padded frame of the token that the roll (attention.py:39) brings to this window slot
+      int pi = wi * g.wh + si - g.shift, pj = wj * g.ww + sj - g.shift;
+      if (pi < 0) pi += g.Hp;
+      if (pj < 0) pj += g.Wp;
+      const bool pad = pi >= g.H || pj >= g.W;
+      if (!pad) code_next = (b * g.H + pi) * g.W + pj;
+      if (g.shift == 0) {
+        kbv_next = pad ? -INFINITY : 0.f;                   // bool key_padding_mask (attention.py:27-35)
+      } else {                                              // float "mask" = rolled activation, channel 0 (attention.py:40)
+        int qi = pi - g.shift, qj = pj - g.shift;
+        if (qi < 0) qi += g.Hp;
+        if (qj < 0) qj += g.Wp;
+        kbv_next = 0.f;
+        if (qi < g.H && qj < g.W) { kb_raw_next = xm[(((long long)b * g.H + qi) * g.W + qj) * g.C]; kb_from_xm_next = true; }
+        if (pad) code_next = -2;                            // x = 0 there: k, v = in-projection bias, and the key stays live
+      }
+    };
+    auto tile_meta_take = [&]() {
+      code = code_next;
+      kbv = kb_from_xm_next ? __bfloat162float(kb_raw_next) * kLog2e : kbv_next;
+    };
+    int it = 0;
+    bool ok = true;
+    if (n_units_my > 0) tile_meta_issue((int)blockIdx.x / g.n_groups);
+    for (int k = 0; ok && k < n_units_my; ++k) {
+      const int u = (int)blockIdx.x + k * (int)gridDim.x;
+      const int grp = u % g.n_groups;
+      tile_meta_take();
+      if (k + 1 < n_units_my) tile_meta_issue((u + (int)gridDim.x) / g.n_groups);      // next unit's gather, ahead of this unit's copies
+      for (int pp = 0; pp < g.ppu; ++pp, ++it) {
+        const int pair = grp * g.ppu + pp, s = it % kStages;
+        lap(0);
+        if (!wait_bar(&empty[s], ((it / kStages) & 1) ^ 1, s_abort, fault, 41)) { ok = false; break; }
+        lap(1);
+        meta_kb[s * 128 + t] = kbv;
+        meta_m[s * 128 + t] = code;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kLoadWarps) : "memory");
+        const uint32_t base = ptx::smem_u32(stages + s * kStageBytes) + dst_off;
+        const bf16* src0 = qkv + pair * 64 + c * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int cd = meta_m[s * 128 + r0 + 16 * i];
+          const uint32_t dst = base + i * (16 * 128);
+          if (cd >= 0) {
+            if (!(g.dbg & 8)) {
+              const bf16* src = src0 + (long long)cd * (3 * g.C);
+              ptx::cp_async_16(dst, src);
+              ptx::cp_async_16(dst + kPanel, src + g.C);
+              ptx::cp_async_16(dst + 2 * kPanel, src + 2 * g.C);
             }
-          } else {
-            kbv = -INFINITY;
+          } else if (cd >= -2) {
+#pragma unroll
+            for (int which = 1; which < 3; ++which) {
+              uint32_t v0 = 0u, v1 = 0u, v2 = 0u, v3 = 0u;
+              if (cd == -2) {
+                const float* bp = b_in + (long long)which * g.C + pair * 64 + c * 8;
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(bp)), b4 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                v0 = pack_bf16(a4.x, a4.y); v1 = pack_bf16(a4.z, a4.w); v2 = pack_bf16(b4.x, b4.y); v3 = pack_bf16(b4.z, b4.w);
+              }
+              ptx::st_shared_v4(dst + which * kPanel, v0, v1, v2, v3);
+            }
           }
         }
-      }
-      if (!wait_bar(&empty[s], ((it / kStages) & 1) ^ 1, s_abort, fault, 41)) break;
-      meta_kb[s * 128 + t] = kbv;
-      meta_m[s * 128 + t] = live ? (int)m : -1;
-      const uint32_t row = ptx::smem_u32(stages + s * kStageBytes) + t * 128;
-      if (live) {
-        const bf16* src = qkv + m * 3 * g.C + pair * 64;
-#pragma unroll
-        for (int which = 0; which < 3; ++which)
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            ptx::cp_async_16(row + which * kPanel + ((c ^ sw) << 4), src + (long long)which * g.C + c * 8);
-      } else if (fill) {
-#pragma unroll
-        for (int which = 1; which < 3; ++which) {
-          const float* bp = b_in + (long long)which * g.C + pair * 64;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t v0 = 0u, v1 = 0u, v2 = 0u, v3 = 0u;
-            if (bias_fill) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(bp + c * 8)), b4 = __ldg(reinterpret_cast<const float4*>(bp + c * 8 + 4));
-              v0 = pack_bf16(a.x, a.y); v1 = pack_bf16(a.z, a.w); v2 = pack_bf16(b4.x, b4.y); v3 = pack_bf16(b4.z, b4.w);
-            }
-            ptx::st_shared_v4(row + which * kPanel + ((c ^ sw) << 4), v0, v1, v2, v3);
-          }
-        }
-      }
-      ptx::cp_async_commit();
-      if (issued > 0) {          // the previous item's copies have landed: publish it (its loads overlapped this item's issue)
-        ptx::cp_async_wait<1>();
+        lap(2);
+        // publish: a plain arrive releases this thread's metadata / fill stores, the cp.async arrive fires when its copies
+        // have landed -- the loader never waits for its own copies and runs up to kStages items ahead
         ptx::fence_proxy_async();
-        ptx::mbar_arrive(&full[prev_s]);
+        ptx::mbar_arrive(&full[s]);
+        ptx::cp_async_mbar_arrive_noinc(&full[s]);
+        lap(3);
       }
-      prev_s = s;
-      ++issued;
     }
-    if (issued > 0) {
-      ptx::cp_async_wait<0>();
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&full[prev_s]);
-    }
+    if (trace != nullptr && t == 0) for (int i = 0; i < 4; ++i) trace[blockIdx.x * 16 + 12 + i] = tacc[i];
   } else if (warp == kMmaWarp) {
     // ===================================================== MMA issuer
     const bool issuer = ptx::elect_one();
@@ -201,16 +235,21 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
     for (int j = 0; ok && j <= n_my; ++j) {
       if (j < n_my) {           // S = q k^T of item j, both heads
         const int s = j % kStages;
+        lap(0);
         if (!wait_bar(&full[s], (j / kStages) & 1, s_abort, fault, 42)) break;
+        lap(1);
+        ptx::fence_proxy_async();      // cp.async-written operands (generic proxy) -> the tensor core's async-proxy reads
         ptx::tc_fence_after();
         const uint64_t q_desc = ptx::smem_desc_sw128(ptx::smem_u32(stages + s * kStageBytes));
         const uint64_t k_desc = q_desc + kPanel / 16;
         for (int h = 0; h < 2; ++h) {
+          lap(0);
           if (!wait_bar(&s_empty[h], (j & 1) ^ 1, s_abort, fault, 43)) { ok = false; break; }
+          lap(2);
           ptx::tc_fence_after();
           if (issuer) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k)      // head h = bytes [64 h, 64 h + 64) of the 128-byte rows, K = 32 = 2 x 16
+            for (int k = 0; k < 2 && !(g.dbg & 4); ++k)      // head h = bytes [64 h, 64 h + 64) of the 128-byte rows, K = 32 = 2 x 16
               ptx::umma_f16(tmem_base + h * 128, q_desc + 4 * h + 2 * k, k_desc + 4 * h + 2 * k, idesc_s, k);
             ptx::umma_commit(&s_full[h]);
           }
@@ -222,14 +261,16 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
         const int i = j - 1, s = i % kStages;
         const uint64_t v_desc = ptx::smem_desc_sw128(ptx::smem_u32(stages + s * kStageBytes + 2 * kPanel));
         for (int h = 0; h < 2; ++h) {
+          lap(0);
           if (!wait_bar(&p_full[h], i & 1, s_abort, fault, 44)) { ok = false; break; }
+          lap(3);
           ptx::tc_fence_after();
           if (issuer) {
             const uint64_t p_desc = ptx::smem_desc_sw128(ptx::smem_u32(pbuf + h * kPBytes));
             uint32_t acc = 0;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {           // 16 keys per step
-              if ((kk * 16) % SLOT >= g.L) continue;   // keys of this step all lie beyond the windows' L tokens: P is 0 there
+              if ((kk * 16) % SLOT >= g.L || (g.dbg & 2)) continue;   // keys of this step all lie beyond the windows' L tokens: P is 0 there
               ptx::umma_f16(tmem_base + 256 + h * kD, p_desc + (kk / 4) * (kPanel / 16) + (kk % 4) * 2,
                             v_desc + kk * (16 * 128 / 16) + 4 * h, idesc_pv, acc);
               acc = 1;
@@ -243,6 +284,8 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
         __syncwarp();
       }
     }
+    lap(0);
+    if (trace != nullptr && lane == 0) for (int i = 0; i < 4; ++i) trace[blockIdx.x * 16 + 8 + i] = tacc[i];
   } else {
     // ===================================================== softmax / epilogue: group = head of the pair
     const int grp = warp >> 2, q = warp & 3;
@@ -254,18 +297,19 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
     // P row of this thread: key columns [w SLOT, w SLOT + L) -> K-panel (w SLOT) / 64, 16-byte chunks from ((w SLOT) % 64) / 8
     const uint32_t p_row = ptx::smem_u32(pbuf + grp * kPBytes) + ((w * SLOT) / 64) * kPanel + row * 128;
     const int chunk0 = ((w * SLOT) % 64) / 8;
-    int m_prev = -1;
+    int m_prev = -1, pair_prev = 0, pair_cur = 0;
     float inv_prev = 0.f;
     bool ok = true;
     auto epilogue = [&](int i) -> bool {                        // O of item i (this group's head) -> att
+      lap(0);
       if (!wait_bar(&pv_done[grp], i & 1, s_abort, fault, 45)) return false;
+      lap(4);
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem_base + lane_off + 256 + grp * kD, o);
       ptx::tmem_ld_wait();
-      if (m_prev >= 0) {
-        const int pair = ((int)blockIdx.x + i * (int)gridDim.x) % g.n_pairs;
-        uint4* dst = reinterpret_cast<uint4*>(att + (long long)m_prev * g.ldo + pair * 64 + grp * kD);
+      if (m_prev >= 0 && !(g.dbg & 16)) {
+        uint4* dst = reinterpret_cast<uint4*>(att + (long long)m_prev * g.ldo + pair_prev * 64 + grp * kD);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           dst[u] = make_uint4(pack_bf16(__uint_as_float(o[8 * u]) * inv_prev, __uint_as_float(o[8 * u + 1]) * inv_prev),
@@ -275,11 +319,17 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
       }
       return true;
     };
-    for (int it = 0; it < n_my; ++it) {
+    for (int it = 0, pp = 0, k = 0; it < n_my; ++it) {
       const int s = it % kStages;
+      if (pp == 0) pair_cur = (((int)blockIdx.x + k * (int)gridDim.x) % g.n_groups) * g.ppu;     // first pair of the unit
+      else ++pair_cur;
+      if (++pp == g.ppu) { pp = 0; ++k; }
+      lap(0);
       if (!wait_bar(&full[s], (it / kStages) & 1, s_abort, fault, 46)) { ok = false; break; }
+      lap(1);
       const int m_cur = meta_m[s * 128 + row];
       if (!wait_bar(&s_full[grp], it & 1, s_abort, fault, 47)) { ok = false; break; }
+      lap(2);
       ptx::tc_fence_after();
       float v[NV];
       {
@@ -300,24 +350,39 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[grp]);           // the next item's S may overwrite the accumulator
+      lap(3);
       // ---- softmax over the window's keys (fp32, exp2 domain)
-      const float* kbp = meta_kb + s * 128 + w * SLOT;
+      const uint32_t kbp = ptx::smem_u32(meta_kb + s * 128 + w * SLOT);
       float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        v[i] = i < g.L ? fmaf(v[i], scale_l2, kbp[i]) : -INFINITY;
-        mx = fmaxf(mx, v[i]);
-      }
-      if (mx == -INFINITY) mx = 0.f;
       float sum = 0.f;
+      if (!(g.dbg & 1)) {
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { v[i] = exp2f(v[i] - mx); sum += v[i]; }
+        for (int i4 = 0; i4 < NV / 4; ++i4) {               // key biases: 16-byte broadcast loads
+          const float4 kb4 = ptx::ld_shared_v4(kbp + i4 * 16);
+          const float kb[4] = {kb4.x, kb4.y, kb4.z, kb4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i4 * 4 + u;
+            v[i] = i < g.L ? fmaf(v[i], scale_l2, kb[u]) : -INFINITY;
+            mx4[u] = fmaxf(mx4[u], v[i]);
+          }
+        }
+        mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (mx == -INFINITY) mx = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[i] = ex2_approx(v[i] - mx); s4[i & 3] += v[i]; }
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
       const float inv = 1.f / sum;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty[s]);               // this stage's metadata has been read
       // ---- previous item of this head: P v has completed (P buffer free), its O leaves through this warp
+      lap(5);
       if (it > 0 && !epilogue(it - 1)) { ok = false; break; }
-      if (m_cur >= 0) {
+      lap(6);
+      if (m_cur >= 0 && !(g.dbg & 32)) {
 #pragma unroll
         for (int c = 0; c < (NV + 7) / 8; ++c) {
           if (c * 8 >= g.L) break;
@@ -332,10 +397,13 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
       ptx::tc_fence_before();            // orders the O read above before the MMA that overwrites the accumulator
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[grp]);
+      lap(7);
       m_prev = m_cur;
+      pair_prev = pair_cur;
       inv_prev = inv;
     }
     if (ok && n_my > 0) epilogue(n_my - 1);
+    if (trace != nullptr && warp == 0 && lane == 0) for (int i = 0; i < 8; ++i) trace[blockIdx.x * 16 + i] = tacc[i];
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -359,6 +427,7 @@ cudaError_t launch_window_attention_tc(TcContext* ctx, const void* qkv, const vo
   AttnGeom g;
   memset(&g, 0, sizeof(g));
   g.B = B; g.H = H; g.W = W; g.C = C; g.wh = win_h; g.ww = win_w; g.shift = shift; g.ldo = ldo;
+  g.dbg = tc_knobs().attn_dbg;
   g.Hp = (H + win_h - 1) / win_h * win_h; g.Wp = (W + win_w - 1) / win_w * win_w;
   g.L = win_h * win_w;
   const int slot = g.L <= 32 ? 32 : 64;
@@ -369,7 +438,18 @@ cudaError_t launch_window_attention_tc(TcContext* ctx, const void* qkv, const vo
   g.n_pairs = C / 64;
   if (n_windows >= (1LL << 31) || n_tiles * g.n_pairs >= (1LL << 31)) return cudaErrorNotSupported;
   g.n_windows = (int)n_windows;
-  g.n_items = (int)(n_tiles * g.n_pairs);
+  // pairs per work unit: whole waves over the SMs first, then as many pairs per unit as possible (the tile's index
+  // arithmetic and key-bias gather are per unit)
+  long long best_cost = -1;
+  for (int ppu = 1; ppu <= g.n_pairs; ++ppu) {
+    if (g.n_pairs % ppu) continue;
+    const long long units = n_tiles * (g.n_pairs / ppu);
+    const long long waves = (units + ctx->num_sms - 1) / ctx->num_sms;
+    const long long cost = waves * (4 * ppu + 1);          // ~ a quarter of an item's time per unit for the index arithmetic
+    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; g.ppu = ppu; }
+  }
+  g.n_groups = g.n_pairs / g.ppu;
+  g.n_units = (int)(n_tiles * g.n_groups);
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -377,10 +457,10 @@ cudaError_t launch_window_attention_tc(TcContext* ctx, const void* qkv, const vo
     if (e != cudaSuccess) return e;
     attr.mark(ctx->device);
   }
-  const int grid = g.n_items < ctx->num_sms ? g.n_items : ctx->num_sms;
+  const int grid = g.n_units < ctx->num_sms ? g.n_units : ctx->num_sms;
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* x = static_cast<const bf16*>(xm);
   bf16* o = static_cast<bf16*>(att);
-  if (slot == 64) return launch_k((window_attention_tc_kernel<64>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev);
-  return launch_k((window_attention_tc_kernel<32>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev);
+  if (slot == 64) return launch_k((window_attention_tc_kernel<64>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev, ctx->trace_dev);
+  return launch_k((window_attention_tc_kernel<32>), dim3(grid), dim3(kThreads), kSmemBytes, st, q, x, b_in, o, g, skip, ctx->fault_dev, ctx->trace_dev);
 }

@@ -769,6 +769,7 @@ const TcKnobs& tc_knobs() {
     t.no_splitk = getenv("LDMB_NO_SPLITK") != nullptr;
     t.mlp_dbg = geti("LDMB_MLP_DBG", 0);
     t.gconv_dbg = geti("LDMB_GCONV_DBG", 0);
+    t.attn_dbg = geti("LDMB_ATTN_DBG", 0);
     return t;
   }();
   return k;

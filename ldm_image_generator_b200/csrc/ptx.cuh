@@ -101,6 +101,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// The mbarrier receives one arrival when all cp.async of this thread issued so far have completed (.noinc: the arrival is
+// part of the barrier's expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
