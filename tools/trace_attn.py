@@ -4,7 +4,7 @@ import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ldm_image_generator_b200 import runtime
 h = runtime.Handle(torch.device("cuda", 0), "bf16")
-B,H,W,Cc,wh,ww,shift = 64,32,32,128,6,6,3
+B,H,W,Cc,wh,ww,shift = 64,32,32,128,6,6,int(os.environ.get("SHIFT","3"))
 qkv = torch.randn(B,H,W,3*Cc,device="cuda").bfloat16(); xm = torch.randn(B,H,W,Cc,device="cuda").bfloat16()
 b_in = torch.randn(3*Cc,device="cuda"); out = torch.empty(B,H,W,4*Cc,device="cuda",dtype=torch.bfloat16)
 for _ in range(3): h.window_attention(qkv,xm,b_in,out[...,3*Cc:],B,H,W,Cc,wh,ww,shift)
