@@ -239,6 +239,12 @@ int ldmb_window_attention(ldmb_handle* h, const void* qkv, const void* xm, const
 int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* w_packed, const float* bias, float* x, int B,
                          int H, int W, int C, int force_generic, void* stream);
 
+/* ChannelNorm + FiLM + grouped 3x3 conv of a SwinBlock fused (unet.py:22,30,42-44; modules.py:23-25), for feature maps that fit
+ * one 128-row tile (8x8, 4x4): xm bf16 [B,H,W,C] = norm(x) * film[:, :C] + film[:, C:]; x fp32 [B,H,W,C] += conv(xm) + bias in place.
+ * film fp32 [H*W][2C]; w_packed as for ldmb_grouped_conv3x3.  LDMB_ERR_UNSUPPORTED for other shapes (the UNet then runs the
+ * separate kernels). */
+int ldmb_normconv(ldmb_handle* h, float* x, const float* film, void* xm, const void* w_packed, const float* bias, int B, int H,
+                  int W, int C, void* stream);
 /* RandomMoE of ReGLU experts (modules.py:14-15,34-36) as one fused kernel, bf16 mode, C = 128 or 256:
  * x fp32 [M,C] += sum over {general, experts e1, e2} of c_e(a_e(xm) * relu(b_e(xm))).
  * w_ab [5*2C, C]: per expert block (general first) the rows of a and b interleaved in chunks of 64 (64 a rows, 64 b rows, ...),

@@ -29,6 +29,12 @@ bool gconv_halo_supported(int B, int H, int W, int C);
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
                               int C, const int* plan, cudaStream_t st);
 
+// ChannelNorm + FiLM + grouped 3x3 conv in one kernel (kernels_normconv.cu) for feature maps that fit one 128-row tile:
+// xm(bf16) = FiLM(norm(x)); x += conv(xm) + bias in place.  plan: {skip,...} of the block or NULL.
+bool normconv_supported(int B, int H, int W, int C);
+cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const int* t_index, void* xm, const void* w, const float* bias,
+                            int B, int H, int W, int C, float eps, const int* plan, cudaStream_t st);
+
 // Fused ReGLU feed-forward (kernels_mlp.cu), C = 128 / 256: x fp32 [M,C] += sum over {general, e1, e2} of
 // c_e(a_e(xm) * relu(b_e(xm))).  Weight layouts as in the two-GEMM path (w_ab [5*2C, C] a|b interleaved in chunks of 64,
 // w_c [w_c_rows >= 5C, C]).  plan: {skip, e1, e2, -} on the device, or NULL to use e1 / e2.

@@ -681,9 +681,17 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   float* x = static_cast<float*>(L.xs.p);
   const float* film = static_cast<const float*>(L.film.p) + (size_t)w.lb * n_t * HW * 2 * C;
   int rc;
+  // Deep levels (an image fits one 128-row tile): ChannelNorm + FiLM + grouped conv in ONE kernel, x updated in place
+  // before the block's GEMMs start (no side stream, no reduction traffic).
+  const bool fused_nc = h->bf16() && !h->force_simt && !(h->skip_mask & ((1u << PK_NORM) | (1u << PK_GCONV))) && normconv_supported(B, Hl, Wl, C);
+  if (fused_nc) {
+    CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim,
+         launch_normconv(h->tc, x, film, u.tindex_dev, u.xm.p, w.w_g, w.b_g, B, Hl, Wl, C, kNormEps, pl, st));
+  } else {
   // ChannelNorm + FiLM (modules.py:23-25, unet.py:22)
   CKLP(PK_NORM, (double)M * C * (4 + h->tsize()),
        launch_norm_film(x, film, u.tindex_dev, u.xm.p, h->bf16(), M, C, HW, kNormEps, pl, st));
+  }
   // grouped 3x3 (unet.py:30): x += conv(xm); the residual stream is only ever added to (x itself is not read),
   // so the conv is forked onto the side stream and joined at the end of the block
   // (only where every concurrent update of x is an L2 reduction: halo conv reds, TMA reduce-add GEMM epilogues)
@@ -702,7 +710,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   }
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
-  const bool fork = u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
+  const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
                     ((fused_ffn && !w.attn) || tc_accum_is_reduction(c));
   if (fork) {
     if (!u.side_stream) {
@@ -714,7 +722,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     CK(cudaStreamWaitEvent(u.side_stream, u.ev_fork, 0));
     if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false))) return rc;
     CK(cudaEventRecord(u.ev_join, u.side_stream));
-  } else if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
+  } else if (!fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
@@ -1442,6 +1450,16 @@ extern "C" int ldmb_grouped_conv3x3(ldmb_handle* h, const void* xm, const void* 
   if (!h || !xm || !w_packed || !bias || !x || B < 1 || H < 1 || W < 1 || C < kHeadDim || C % kHeadDim) return LDMB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   return grouped_conv(h, xm, w_packed, bias, x, B, H, W, C, nullptr, static_cast<cudaStream_t>(stream), force_generic != 0);
+}
+
+extern "C" int ldmb_normconv(ldmb_handle* h, float* x, const float* film, void* xm, const void* w_packed, const float* bias, int B,
+                             int H, int W, int C, void* stream) {
+  if (!h || !x || !film || !xm || !w_packed || !bias || B < 1 || H < 1 || W < 1) return LDMB_ERR_INVALID;
+  if (!h->bf16() || !normconv_supported(B, H, W, C)) return fail(h, LDMB_ERR_UNSUPPORTED, "fused norm + conv: bf16 mode, power-of-two feature maps that fit one 128-row tile, C/64 in {1,2,4,8,16}");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKLP(PK_GCONV, 2.0 * B * H * W * (double)C * 9 * kHeadDim, launch_normconv(h->tc, x, film, nullptr, xm, w_packed, bias, B, H, W, C, kNormEps, nullptr, st));
+  return LDMB_OK;
 }
 
 extern "C" int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,

@@ -229,6 +229,10 @@ class Handle:
         self.check(self.lib.ldmb_mlp_fused(self.h, xm.data_ptr(), w_ab.data_ptr(), b_ab.data_ptr(), w_c.data_ptr(), b_c.data_ptr(),
                                            x.data_ptr(), M, Cc, e1, e2, stream_ptr(self.device)))
 
+    def normconv(self, x, film, xm, w_packed, bias, B, H, W, Cc) -> None:
+        self.check(self.lib.ldmb_normconv(self.h, x.data_ptr(), film.data_ptr(), xm.data_ptr(), w_packed.data_ptr(), bias.data_ptr(),
+                                          B, H, W, Cc, stream_ptr(self.device)))
+
     def grouped_conv3x3(self, xm, w_packed, bias, x, B, H, W, Cc, force_generic=False) -> None:
         self.check(self.lib.ldmb_grouped_conv3x3(self.h, xm.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), x.data_ptr(),
                                                  B, H, W, Cc, int(force_generic), stream_ptr(self.device)))

@@ -209,6 +209,33 @@ def test_grouped_conv3x3_accumulates_into_residual(handles, B, H, W, C, generic)
     assert _rel(x - x0, ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W,C", [(64, 8, 8, 512), (64, 4, 4, 1024), (3, 8, 8, 512), (7, 4, 4, 1024), (5, 8, 8, 256), (130, 4, 4, 512),
+                                     (2, 8, 8, 128), (9, 4, 4, 64), (300, 8, 8, 512), (1, 2, 2, 1024)])
+def test_normconv_fused_kernel(handles, B, H, W, C):
+    """ChannelNorm + FiLM + grouped conv in one kernel (cluster statistics exchange, in-place residual update) vs torch:
+    xm against the fp32 formula (bf16 rounding), the residual update against F.conv2d of the kernel's own bf16 xm."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(B * 11 + H * 5 + C)
+    x0 = torch.randn(B, H, W, C, device="cuda", generator=g) * 2 + 0.5
+    film = torch.randn(H * W, 2 * C, device="cuda", generator=g)
+    w = (torch.randn(C, 32, 3, 3, device="cuda", generator=g) / 288 ** 0.5).bfloat16()
+    b = torch.randn(C, device="cuda", generator=g)
+    x = x0.clone()
+    xm = torch.full((B, H, W, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    h.normconv(x, film, xm, _pack_grouped(w), b, B, H, W, C)
+    assert h.device_fault() == 0
+    xn = (x0 - x0.mean(-1, keepdim=True)) / torch.sqrt(x0.var(-1, keepdim=True) + 1e-4)
+    f = film.reshape(1, H, W, 2 * C)
+    want_xm = xn * f[..., :C] + f[..., C:]
+    assert _rel(xm.float(), want_xm) < 4e-3
+    ref = F.conv2d(xm.float().permute(0, 3, 1, 2), w.float(), b, padding=1, groups=C // 32).permute(0, 2, 3, 1)
+    assert _rel(x - x0, ref) < 1e-5
+    # and the separate kernels produce the same xm bit for bit up to the statistics' summation order
+    xm2 = torch.empty_like(xm)
+    h.channelnorm_film(x0.reshape(-1, C), film, xm2.reshape(-1, C), B * H * W, C, H * W)
+    assert _rel(xm.float(), xm2.float()) < 2e-3
+
+
 @pytest.mark.parametrize("M,C,e1,e2", [(256, 128, 0, 1), (4096, 128, 3, 2), (1000, 128, 1, 3), (65536, 128, 2, 0), (512, 256, 0, 3),
                                        (16384, 256, 3, 1), (700, 256, 2, 1)])
 def test_mlp_fused_kernel(handles, M, C, e1, e2):
