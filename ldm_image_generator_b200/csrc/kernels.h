@@ -26,12 +26,18 @@ int tc_trace_read(TcContext* ctx, long long* host, int max_ctas);
 // Grouped 3x3 convolution with one halo-patch load per tile (kernels_gconv.cu): x fp32 [B,H,W,C] += conv(xm) + bias;
 // w packed as block-diagonal pairs of 32-channel groups [C/64][64][9*64].  plan: {skip,...} of the block or NULL.
 bool gconv_halo_supported(int B, int H, int W, int C);
+// max_ctas > 0 caps the persistent grid (rounded down to a whole number of channel slices): the conv then fits beside a GEMM
+// that leaves that many SMs idle
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                              int C, const int* plan, cudaStream_t st);
+                              int C, const int* plan, cudaStream_t st, int max_ctas = 0);
+// CTAs launch_gemm_tc puts on the machine for this GEMM (0: not a tcgen05 shape)
+int tc_gemm_ctas(TcContext* ctx, const GemmDesc& d);
+int tc_num_sms(const TcContext* ctx);
 
 // ChannelNorm + FiLM + grouped 3x3 conv in one kernel (kernels_normconv.cu) for feature maps that fit one 128-row tile:
 // xm(bf16) = FiLM(norm(x)); x += conv(xm) + bias in place.  plan: {skip,...} of the block or NULL.
 bool normconv_supported(int B, int H, int W, int C);
+bool normconv_in_step();      // whether the UNet step uses it (environment knob; off: it is slower than the separate kernels today)
 cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const int* t_index, void* xm, const void* w, const float* bias,
                             int B, int H, int W, int C, float eps, const int* plan, cudaStream_t st);
 

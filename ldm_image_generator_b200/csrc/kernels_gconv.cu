@@ -253,11 +253,12 @@ bool gconv_halo_supported(int B, int H, int W, int C) {
 
 // x fp32 [B,H,W,C] += conv3x3(xm bf16 [B,H,W,C], grouped by 32) + bias; w packed [C/64][64][9*64] block-diagonal pairs.
 static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res);
+                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res,
+                                      int max_ctas = 0);
 
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                              int C, const int* plan, cudaStream_t st) {
-  return launch_halo_common(ctx, xm, w, bias, x, B, H, W, C, plan, st, 0, 0.f, nullptr, nullptr);
+                              int C, const int* plan, cudaStream_t st, int max_ctas) {
+  return launch_halo_common(ctx, xm, w, bias, x, B, H, W, C, plan, st, 0, 0.f, nullptr, nullptr, max_ctas);
 }
 
 bool conv64_halo_supported(int C, int N) { return g_gconv_mode != 0 && C == kSlice && N == kSlice; }
@@ -271,7 +272,8 @@ cudaError_t launch_conv64_halo(TcContext* ctx, const void* in, const void* w, co
 }
 
 static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res) {
+                                      int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res,
+                                      int max_ctas) {
   GconvGeom g;
   memset(&g, 0, sizeof(g));
   g.B = B; g.H = H; g.W = W; g.C = C;
@@ -327,6 +329,7 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
   const int nz = C / kSlice;
   const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;
   int per_z = ctx->num_sms / nz;
+  if (max_ctas > 0 && max_ctas / nz < per_z) per_z = max_ctas / nz;
   if (per_z > n_sp) per_z = n_sp;
   if (per_z < 1) per_z = 1;
   cudaLaunchConfig_t cfg;

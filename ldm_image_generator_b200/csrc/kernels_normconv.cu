@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
 __global__ void __launch_bounds__(kThreads, 1)
 normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, const float* __restrict__ film,
                 const int* __restrict__ t_index, bf16* __restrict__ xm, const float* __restrict__ bias, const NcGeom g,
-                const int* __restrict__ plan, int* fault) {
+                const int* __restrict__ plan, int* fault, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wts = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* patches = wts + g.S * kWBytes;
@@ -83,6 +83,10 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
   uint64_t* mma_done = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  auto stamp = [&](int slot) {     // debug (ldmb_debug_tc_trace): %globaltimer at the phase boundaries, thread 0 of every CTA
+    if (trace != nullptr && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[blockIdx.x * 16 + slot] = t; }
+  };
+  stamp(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = g.CL > 1 ? ptx::cluster_ctarank() : 0u;
   const int cl = blockIdx.x / g.CL;
@@ -102,6 +106,7 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  stamp(1);
   const uint32_t tmem_base = *tmem_slot;
   const bool skip_block = plan != nullptr && plan[0] != 0;       // stochastic depth (unet.py:39-40)
   // weights are older than the previous kernel: requested before waiting on it
@@ -112,7 +117,9 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
         ptx::tma_load_2d(wts + s * kWBytes + tap * kWTile, &tmW, wbar, tap * kSlice, ((int)rank * g.S + s) * kSlice);
   }
   if (g.CL > 1) ptx::cluster_sync();         // every CTA of the cluster is resident before anyone writes into its smem
+  stamp(2);
   pdl_wait();
+  stamp(3);
 
   const int tiles_per_pass = g.n_clusters * g.R;
   const int rounds = skip_block ? 0 : (g.n_tiles + tiles_per_pass - 1) / tiles_per_pass;
@@ -149,39 +156,64 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
         st_cluster_f2(g.CL > 1 ? mapa(local, (uint32_t)l16) : local, mean, m2);
       }
     }
+    if (r == 0) stamp(4);
     if (g.CL > 1) ptx::cluster_sync(); else __syncthreads();
+    if (r == 0) stamp(5);
     // ---------------- phase B: merge the partials, normalise + FiLM, -> xm (global) and the halo patch (smem)
+    // (plain C++ loads / stores, no asm barriers: the FiLM loads of later units are free to issue ahead of earlier units' stores)
+    float mean_k[kNV], rs_k[kNV];
 #pragma unroll
     for (int k = 0; k < kNV; ++k) {
       const int u = hw + 16 * k;
-      const int s = u & (g.S - 1), slot = u >> g.s_shift, p = slot & (g.HW - 1), ti = slot >> g.hw_shift;
+      const int slot = u >> g.s_shift;
       float2 part = make_float2(0.f, 0.f);
       if (u < g.NU && l16 < n_part) part = st_cur[l16 * g.slots + slot];
       const float mean = half_warp_sum(part.x) / (float)n_part;
       const float dm = l16 < n_part ? part.x - mean : 0.f;
       const float m2 = half_warp_sum(part.y + (float)kSlice * dm * dm);       // Chan et al.: M2 = sum M2_i + n_i (mean_i - mean)^2
-      const float rs = 1.f / sqrtf(m2 * inv_c1 + g.eps);                      // unbiased variance (modules.py:24)
-      if (pix[k] >= 0) {
-        const int b = pix[k] >> g.hw_shift, c0 = ((int)rank * g.S + s) * kSlice + l16 * 4;
-        const int trow = t_index != nullptr ? t_index[b] : 0;
-        const float* fr = film + ((long long)trow * g.HW + p) * 2 * g.C + c0;
-        const float4 mu = __ldg(reinterpret_cast<const float4*>(fr)), bi = __ldg(reinterpret_cast<const float4*>(fr + g.C));
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((v[k].x - mean) * rs, mu.x, bi.x), fmaf((v[k].y - mean) * rs, mu.y, bi.y));
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((v[k].z - mean) * rs, mu.z, bi.z), fmaf((v[k].w - mean) * rs, mu.w, bi.w));
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(xm + (long long)pix[k] * g.C + c0) = pk;
-        // patch row of pixel (y, x) of image ib in its tile: ib * per_img + (y + 1) * pitch + (x + 1); 8 channels = one 16-byte chunk
-        const int prow = (ti % g.TB) * g.per_img + ((p >> g.w_shift) + 1) * g.pitch + ((p & (g.W - 1)) + 1);
-        const uint32_t dst = ptx::smem_u32(patches + ((ti / g.TB) * g.S + s) * g.patch_bytes) + prow * 128 +
-                             ((((l16 >> 1) ^ (prow & 7))) << 4) + (l16 & 1) * 8;
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pk.x), "r"(pk.y) : "memory");
+      mean_k[k] = mean;
+      rs_k[k] = 1.f / sqrtf(m2 * inv_c1 + g.eps);                             // unbiased variance (modules.py:24)
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < kNV; k0 += 4) {
+      float4 mu[4], bi[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk, u = hw + 16 * k;
+        if (pix[k] >= 0) {
+          const int s = u & (g.S - 1), p = (u >> g.s_shift) & (g.HW - 1);
+          const int b = pix[k] >> g.hw_shift, c0 = ((int)rank * g.S + s) * kSlice + l16 * 4;
+          const int trow = t_index != nullptr ? t_index[b] : 0;
+          const float* fr = film + ((long long)trow * g.HW + p) * 2 * g.C + c0;
+          mu[kk] = __ldg(reinterpret_cast<const float4*>(fr));
+          bi[kk] = __ldg(reinterpret_cast<const float4*>(fr + g.C));
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk, u = hw + 16 * k;
+        if (pix[k] >= 0) {
+          const int s = u & (g.S - 1), slot = u >> g.s_shift, p = slot & (g.HW - 1), ti = slot >> g.hw_shift;
+          const int c0 = ((int)rank * g.S + s) * kSlice + l16 * 4;
+          const float mean = mean_k[k], rs = rs_k[k];
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((v[k].x - mean) * rs, mu[kk].x, bi[kk].x), fmaf((v[k].y - mean) * rs, mu[kk].y, bi[kk].y));
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((v[k].z - mean) * rs, mu[kk].z, bi[kk].z), fmaf((v[k].w - mean) * rs, mu[kk].w, bi[kk].w));
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(xm + (long long)pix[k] * g.C + c0) = pk;
+          // patch row of pixel (y, x) of image ib in its tile: ib * per_img + (y + 1) * pitch + (x + 1); 8 channels = one 16-byte chunk
+          const int prow = (ti % g.TB) * g.per_img + ((p >> g.w_shift) + 1) * g.pitch + ((p & (g.W - 1)) + 1);
+          uint8_t* dst = patches + ((ti / g.TB) * g.S + s) * g.patch_bytes + prow * 128 + (((l16 >> 1) ^ (prow & 7)) << 4) + (l16 & 1) * 8;
+          *reinterpret_cast<uint2*>(dst) = pk;
+        }
       }
     }
+    if (r == 0) stamp(6);
     ptx::fence_proxy_async();          // generic-proxy smem writes -> the tensor core's async-proxy reads
     ptx::tc_fence_before();
     __syncthreads();
+    if (r == 0) stamp(7);
     // ---------------- phase C: the nine taps of every (tile, slice) of the round, one warp issues
     if (warp == 0) {
       ptx::tc_fence_after();
@@ -214,29 +246,47 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
     }
     // ---------------- phase D: x += accumulator + bias for the valid patch rows (plain stores: single owner)
     if (!wait_bar(mma_done, r & 1, s_abort, fault, 52)) break;
+    if (r == 0) stamp(8);
     ptx::tc_fence_after();
     {
       const int q = warp & 3, half = warp >> 2;                  // TMEM lane quadrant, 32-column half of the slice
       const int i = q * 32 + lane;                               // patch row
       const int ib = i / g.per_img, rr = i % g.per_img, yy = rr / g.pitch, xx = rr % g.pitch;
-      for (int j = 0; j < g.R; ++j) {
-        const int tile = tile0 + j, b = tile * g.TB + ib;
-        const bool valid = tile < g.n_tiles && ib < g.TB && b < g.B && yy < g.H && xx < g.W;
-        for (int s = 0; s < g.S; ++s) {
+      const bool row_ok = ib < g.TB && yy < g.H && xx < g.W;
+      // two (tile, slice) accumulators at a time: both rows of x are requested before either accumulator is read
+      const int n_acc = g.R * g.S;
+      for (int a0 = 0; a0 < n_acc; a0 += 2) {
+        float4 cur[2][8];
+        float* xr[2];
+        bool valid[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int a = a0 + e, j = a >> g.s_shift, s = a & (g.S - 1);
+          const int tile = tile0 + j, b = tile * g.TB + ib;
+          valid[e] = a < n_acc && row_ok && tile < g.n_tiles && b < g.B;
+          const int c0 = ((int)rank * g.S + s) * kSlice + half * 32;
+          xr[e] = x + ((long long)(b * g.HW + yy * g.W + xx)) * g.C + c0;
+          if (valid[e]) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[e][u] = *reinterpret_cast<const float4*>(xr[e] + 4 * u);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int a = a0 + e, s = a & (g.S - 1);
+          if (a >= n_acc) break;                                   // uniform
           uint32_t acc[32];
-          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (j * g.S + s) * kSlice + half * 32, acc);
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * kSlice + half * 32, acc);
           ptx::tmem_ld_wait();
-          if (valid) {
-            const int c0 = ((int)rank * g.S + s) * kSlice + half * 32;
-            float* xr = x + ((long long)(b * g.HW + yy * g.W + xx)) * g.C + c0;
-            const float* bz = bias + c0;
+          if (valid[e]) {
+            const float* bz = bias + ((int)rank * g.S + s) * kSlice + half * 32;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + 4 * u));
-              float4 cur = *reinterpret_cast<const float4*>(xr + 4 * u);
-              cur.x += __uint_as_float(acc[4 * u]) + bb.x; cur.y += __uint_as_float(acc[4 * u + 1]) + bb.y;
-              cur.z += __uint_as_float(acc[4 * u + 2]) + bb.z; cur.w += __uint_as_float(acc[4 * u + 3]) + bb.w;
-              *reinterpret_cast<float4*>(xr + 4 * u) = cur;
+              float4 c4 = cur[e][u];
+              c4.x += __uint_as_float(acc[4 * u]) + bb.x; c4.y += __uint_as_float(acc[4 * u + 1]) + bb.y;
+              c4.z += __uint_as_float(acc[4 * u + 2]) + bb.z; c4.w += __uint_as_float(acc[4 * u + 3]) + bb.w;
+              *reinterpret_cast<float4*>(xr[e] + 4 * u) = c4;
             }
           }
         }
@@ -245,10 +295,12 @@ normconv_kernel(const __grid_constant__ CUtensorMap tmW, float* __restrict__ x, 
     ptx::tc_fence_before();
     __syncthreads();               // TMEM and the patches are free for the next round
     ptx::tc_fence_after();
+    if (r == 0) stamp(9);
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (g.CL > 1) ptx::cluster_sync();         // no CTA leaves while a peer may still write statistics into its smem
+  stamp(10);
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -294,12 +346,17 @@ bool plan_geom(int num_sms, int B, int H, int W, int C, NcGeom& g, int& smem) {
 
 }  // namespace
 
-static const bool g_normconv = getenv("LDMB_NORMCONV") == nullptr || atoi(getenv("LDMB_NORMCONV")) != 0;   // debug: 0 = separate kernels
+// Off in the UNet step by default (LDMB_NORMCONV=1 turns it on): as it stands one round of the kernel takes ~28 us at the level-2
+// shape -- its phases run back to back on 8 warps with 255 registers each, nothing hides their latency -- against 5 us + 9 us for
+// the separate kernels.  The kernel-level entry point (ldmb_normconv) and its parity tests always run it.
+static const bool g_normconv_in_step = getenv("LDMB_NORMCONV") != nullptr && atoi(getenv("LDMB_NORMCONV")) != 0;
+
+bool normconv_in_step() { return g_normconv_in_step; }
 
 bool normconv_supported(int B, int H, int W, int C) {
   NcGeom g;
   int smem;
-  return g_normconv && B >= 1 && H >= 1 && W >= 1 && (long long)B * H * W < (1LL << 30) && plan_geom(148, B, H, W, C, g, smem);
+  return B >= 1 && H >= 1 && W >= 1 && (long long)B * H * W < (1LL << 30) && plan_geom(148, B, H, W, C, g, smem);
 }
 
 // xm bf16 [B,H,W,C] = FiLM(ChannelNorm(x)); x fp32 [B,H,W,C] += conv3x3(xm, groups of 32) + bias.
@@ -308,7 +365,7 @@ cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const i
                             int B, int H, int W, int C, float eps, const int* plan, cudaStream_t st) {
   NcGeom g;
   int smem;
-  if (!g_normconv || !plan_geom(ctx->num_sms, B, H, W, C, g, smem)) return cudaErrorNotSupported;
+  if (!plan_geom(ctx->num_sms, B, H, W, C, g, smem)) return cudaErrorNotSupported;
   g.eps = eps;
   CUtensorMap tmW;
   {
@@ -331,8 +388,24 @@ cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const i
   cfg.gridDim = dim3(g.n_clusters * g.CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int na = 0;
-  if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   if (g.CL > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = g.CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
   cfg.attrs = at; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, normconv_kernel, tmW, x, film, t_index, static_cast<bf16*>(xm), bias, g, plan, ctx->fault_dev);
+  // Clusters beyond what the GPU holds at once would run as a second wave of the whole kernel: cap the grid at the co-resident
+  // count (a cluster needs CL free SMs in ONE GPC) and let the rounds loop cover the rest.  Cached per (cluster size, smem).
+  static int max_active[16][4] = {};
+  const int key = g.CL == 8 ? 3 : (g.CL == 4 ? 2 : (g.CL == 2 ? 1 : 0));
+  int& cached = max_active[ctx->device & 15][key];
+  if (cached == 0) {
+    int n = 0;
+    cfg.dynamicSmemBytes = 232448;
+    if (g.CL > 1 && cudaOccupancyMaxActiveClusters(&n, normconv_kernel, &cfg) == cudaSuccess && n > 0) cached = n;
+    else cached = ctx->num_sms / g.CL;
+    cfg.dynamicSmemBytes = smem;
+  }
+  if (g.n_clusters > cached) {
+    g.n_clusters = cached;
+    cfg.gridDim = dim3(g.n_clusters * g.CL);
+  }
+  if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; cfg.numAttrs = na; }
+  return cudaLaunchKernelEx(&cfg, normconv_kernel, tmW, x, film, t_index, static_cast<bf16*>(xm), bias, g, plan, ctx->fault_dev, ctx->trace_dev);
 }

@@ -717,6 +717,7 @@ int tc_trace_read(TcContext* ctx, long long* host, int max_ctas) {
 
 void tc_set_splitk(TcContext* ctx, bool on) { ctx->splitk = on; }
 
+int tc_num_sms(const TcContext* ctx) { return ctx->num_sms; }
 int tc_poll_fault(const TcContext* ctx) { return ctx->fault_host ? *ctx->fault_host : 0; }
 
 int tc_read_fault(TcContext* ctx, cudaStream_t s) {
@@ -775,7 +776,15 @@ const TcKnobs& tc_knobs() {
   return k;
 }
 
-cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
+static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaStream_t s, int* ctas_only);
+cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) { return launch_gemm_tc_impl(ctx, d, s, nullptr); }
+int tc_gemm_ctas(TcContext* ctx, const GemmDesc& d) {
+  int n = 0;
+  return launch_gemm_tc_impl(ctx, d, nullptr, &n) == cudaSuccess ? n : 0;
+}
+
+// ctas_only != NULL: dry run -- only reports the grid the launch would use
+static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaStream_t s, int* ctas_only) {
   if (!tc_supported(d)) return cudaErrorNotSupported;
   int bn = pick_bn(d, ctx->num_sms);
   const int batch = d.batch > 0 ? d.batch : 1;
@@ -892,6 +901,11 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmDesc& d, cudaStream_t s) {
       tl.splits = (tl.num_kb + tl.kb_per - 1) / tl.kb_per;
       tl.total *= tl.splits;
     }
+  }
+  if (ctas_only != nullptr) {
+    const int grid = tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg;
+    *ctas_only = grid;
+    return cudaSuccess;
   }
   if (d.amode == AM_ROWS)
     return cg == 2 ? launch_tc_bn<AM_ROWS, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_ROWS, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);

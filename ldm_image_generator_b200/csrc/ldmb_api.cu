@@ -99,6 +99,10 @@ struct UNetState {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_conv = getenv("LDMB_NO_FORK") == nullptr;
+  // where the forked conv runs in the two-GEMM blocks (C >= 512): 1 (default) = from the norm on, beside the a|b GEMM; 2 = beside
+  // the c-projection only, capped to the SMs that GEMM's grid leaves idle -- measured 22 % SLOWER end to end (16 CTAs walk 32 tiles
+  // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt)
+  int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 1;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -240,10 +244,10 @@ int window_attention(ldmb_handle* h, const void* qkv, const void* xm, const floa
 // x fp32 [B,H,W,C] += grouped conv3x3(xm) + bias (unet.py:30: groups of 32 channels).
 // tcgen05, halo-patch kernel (every activation read once) when C % 64 == 0, else the generic implicit-GEMM path.
 int grouped_conv(ldmb_handle* h, const void* xm, const void* w_g, const float* b_g, float* x, int B, int Hl, int Wl, int C,
-                 const int* pl, cudaStream_t st, bool force_generic) {
+                 const int* pl, cudaStream_t st, bool force_generic, int max_ctas = 0) {
   const int M = B * Hl * Wl;
   if (h->bf16() && !h->force_simt && !force_generic && gconv_halo_supported(B, Hl, Wl, C)) {
-    CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim, launch_gconv_halo(h->tc, xm, w_g, b_g, x, B, Hl, Wl, C, pl, st));
+    CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim, launch_gconv_halo(h->tc, xm, w_g, b_g, x, B, Hl, Wl, C, pl, st, max_ctas));
     return LDMB_OK;
   }
   GemmDesc d = gd();
@@ -683,7 +687,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   int rc;
   // Deep levels (an image fits one 128-row tile): ChannelNorm + FiLM + grouped conv in ONE kernel, x updated in place
   // before the block's GEMMs start (no side stream, no reduction traffic).
-  const bool fused_nc = h->bf16() && !h->force_simt && !(h->skip_mask & ((1u << PK_NORM) | (1u << PK_GCONV))) && normconv_supported(B, Hl, Wl, C);
+  const bool fused_nc = h->bf16() && !h->force_simt && !(h->skip_mask & ((1u << PK_NORM) | (1u << PK_GCONV))) && normconv_in_step() && normconv_supported(B, Hl, Wl, C);
   if (fused_nc) {
     CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim,
          launch_normconv(h->tc, x, film, u.tindex_dev, u.xm.p, w.w_g, w.b_g, B, Hl, Wl, C, kNormEps, pl, st));
@@ -712,17 +716,30 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
                     ((fused_ffn && !w.attn) || tc_accum_is_reduction(c));
-  if (fork) {
-    if (!u.side_stream) {
-      CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&u.ev_join, cudaEventDisableTiming));
-    }
+  if (fork && !u.side_stream) {
+    CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&u.ev_join, cudaEventDisableTiming));
+  }
+  // Late fork (two-GEMM blocks): the conv starts with the c-projection, whose grid (output tiles x split-K) leaves some SMs idle,
+  // and is capped to those -- beside the a|b GEMM it would take SMs that GEMM's persistent CTAs then wait for.
+  int conv_cap = 0;
+  if (fork && !fused_ffn && u.fork_mode == 2) {
+    conv_cap = tc_num_sms(h->tc) - tc_gemm_ctas(h->tc, c);
+    if (conv_cap < C / 64) conv_cap = 0;                     // fewer idle SMs than channel slices: fork early instead
+  }
+  const bool late = conv_cap > 0;
+  auto fork_conv_now = [&](int cap) -> int {
     CK(cudaEventRecord(u.ev_fork, st));
     CK(cudaStreamWaitEvent(u.side_stream, u.ev_fork, 0));
-    if ((rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false))) return rc;
+    int rc2 = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false, cap);
+    if (rc2) return rc2;
     CK(cudaEventRecord(u.ev_join, u.side_stream));
-  } else if (!fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
+    return LDMB_OK;
+  };
+  if (fork && !late) {
+    if ((rc = fork_conv_now(0))) return rc;
+  } else if (!fork && !fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
@@ -747,6 +764,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_stride = 2 * C; d.plan = pl;
     if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
+    if (late && (rc = fork_conv_now(conv_cap))) return rc;
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
   if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
