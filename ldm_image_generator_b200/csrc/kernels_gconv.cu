@@ -34,6 +34,8 @@ struct GconvGeom {
   int TW, TH, TB, pitch;                   // tile: TB images x TH rows x TW columns; patch pitch = TW + 2
   int w_tiles, h_tiles, b_tiles;           // spatial tiling
   int a_bytes, stage_bytes, stages;
+  int out_rows, out_half, out_bytes;       // staged residual update: TB*TH*TW compact rows x 2 halves of 32 fp32 channels, each half
+                                           // 1024-aligned (swizzle phase); out_bytes = 2 * out_half (0: red.global path)
   int dbg;                                 // debug experiments: 1 = no reds, 2 = one tap only
   // dense mode (VAE 3x3 conv with 64 input and 64 output channels, vae.py:57-58): out(bf16) = act(acc + bias) (+ res)
   int dense; float slope; bf16* out; const bf16* res;
@@ -66,12 +68,14 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, float* __restrict__ x,
+gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                  float* __restrict__ x,
                   const float* __restrict__ bias, const GconvGeom g, const int* __restrict__ plan, int* fault, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wts = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = wts + kWBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(stages + g.stages * g.stage_bytes);
+  uint8_t* outbuf = stages + g.stages * g.stage_bytes;            // 2 x out_bytes, 1024-aligned (stage_bytes is a multiple of 1024)
+  uint64_t* full = reinterpret_cast<uint64_t*>(outbuf + 2 * g.out_bytes);
   uint64_t* empty = full + 4;
   uint64_t* tfull = empty + 4;
   uint64_t* tempty = tfull + 2;
@@ -89,6 +93,7 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmW);
+    if (g.out_bytes) ptx::prefetch_tensormap(&tmX);
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, 128); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
@@ -183,7 +188,14 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int img = i / per_img, r = i % per_img, yy = r / g.pitch, xx = r % g.pitch;
     const float* bz = bias + z * kSlice;
     uint32_t as = 0, aphase = 0;
-    for (int sp = sp0; sp < sp_end; sp += sp_step) {
+    const bool staged = g.out_bytes != 0;
+    // staged residual update: the tile's valid rows are packed ([image][y][x], 128-byte rows of 32 fp32 channels, two halves,
+    // 128B-swizzled) and added to x by TWO bulk tensor reduce-adds per tile instead of 16 red.global.add.v4 per pixel
+    const int cr = (img * g.TH + yy) * g.TW + xx;                  // compact row of this thread's pixel
+    const bool in_tile = img < g.TB && yy < g.TH && xx < g.TW;
+    const uint32_t sw = static_cast<uint32_t>(cr & 7);
+    int n_done = 0;
+    for (int sp = sp0; sp < sp_end; sp += sp_step, ++n_done) {
       const int wt = sp % g.w_tiles, ht = (sp / g.w_tiles) % g.h_tiles, bt = sp / (g.w_tiles * g.h_tiles);
       const int b = bt * g.TB + img, hh = ht * g.TH + yy, ww = wt * g.TW + xx;
       const bool valid = img < g.TB && b < g.B && yy < g.TH && hh < g.H && xx < g.TW && ww < g.W;
@@ -193,6 +205,11 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (threadIdx.x == 64) trace_stamp(trace, sp == sp0 ? 6 : 7);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kSlice;
+      uint8_t* ob = outbuf + (n_done & 1) * g.out_bytes;
+      if (staged && !g.dense) {
+        if (threadIdx.x == 64) ptx::bulk_wait_read<1>();           // the reduce that last read this buffer (two tiles ago) is done with it
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -219,6 +236,16 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint4* op = reinterpret_cast<uint4*>(g.out + pix + half * 32);
 #pragma unroll
           for (int u = 0; u < 4; ++u) op[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        } else if (staged && !g.dense) {
+          if (in_tile) {
+            const uint32_t srow = ptx::smem_u32(ob) + half * g.out_half + cr * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bz + half * 32 + 4 * u));
+              ptx::st_shared_v4(srow + ((u ^ sw) << 4), __float_as_uint(__uint_as_float(v[4 * u]) + bb.x), __float_as_uint(__uint_as_float(v[4 * u + 1]) + bb.y),
+                                __float_as_uint(__uint_as_float(v[4 * u + 2]) + bb.z), __float_as_uint(__uint_as_float(v[4 * u + 3]) + bb.w));
+            }
+          }
         } else if (valid && !(g.dbg & 1)) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -231,9 +258,19 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      if (staged && !g.dense) {
+        ptx::fence_proxy_async();                                  // generic-proxy staging writes -> the bulk reduce's async-proxy reads
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (threadIdx.x == 64 && !(g.dbg & 1)) {                   // rows / images beyond the tensor are clipped by the tensor map
+          ptx::tma_reduce_add_4d(&tmX, ob, z * kSlice, wt * g.TW, ht * g.TH, bt * g.TB);
+          ptx::tma_reduce_add_4d(&tmX, ob + g.out_half, z * kSlice + 32, wt * g.TW, ht * g.TH, bt * g.TB);
+          ptx::bulk_commit();
+        }
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (staged && !g.dense && threadIdx.x == 64) ptx::bulk_wait_read<0>();     // the staging buffers stay valid until they have been read
   }
   if (threadIdx.x == 64) trace_stamp(trace, 8);
   ptx::tc_fence_before();
@@ -295,7 +332,16 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
   int need_rows = 128 + 2 * g.pitch + 2;                   // rows the nine descriptors can touch
   if (need_rows < box_rows) need_rows = box_rows;
   g.stage_bytes = ((need_rows * 128 + 1023) / 1024) * 1024;
-  const int avail = 232448 - 1024 - kWBytes - 256;
+  // staged residual update (grouped mode): compact rows x 2 halves, double buffered
+  g.out_rows = g.TB * g.TH * g.TW;
+  g.out_bytes = 0; g.out_half = 0;
+  static const bool stage_out = getenv("LDMB_GCONV_RED") == nullptr;             // debug: LDMB_GCONV_RED=1 = red.global.add epilogue
+  if (!dense && stage_out && g.out_rows <= 128 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 && C % 4 == 0)
+  {
+    g.out_half = ((g.out_rows * 128 + 1023) / 1024) * 1024;
+    g.out_bytes = 2 * g.out_half;
+  }
+  const int avail = 232448 - 1024 - kWBytes - 256 - 2 * g.out_bytes;
   g.stages = avail / g.stage_bytes;
   if (g.stages > 4) g.stages = 4;
   if (g.stages < 1) return cudaErrorNotSupported;
@@ -319,7 +365,17 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  const int smem = 1024 + kWBytes + g.stages * g.stage_bytes + 256;
+  CUtensorMap tmX;
+  memset(&tmX, 0, sizeof(tmX));
+  if (g.out_bytes) {
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * W, (cuuint64_t)C * 4 * W * H};
+    const cuuint32_t box[4] = {32, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TB};
+    if (ctx->encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  const int smem = 1024 + kWBytes + g.stages * g.stage_bytes + 2 * g.out_bytes + 256;
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(gconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -339,5 +395,5 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_ldmb_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gconv_halo_kernel, tmA, tmW, x, bias, g, plan, ctx->fault_dev, ctx->trace_dev);
+  return cudaLaunchKernelEx(&cfg, gconv_halo_kernel, tmA, tmW, tmX, x, bias, g, plan, ctx->fault_dev, ctx->trace_dev);
 }
