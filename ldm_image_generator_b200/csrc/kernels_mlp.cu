@@ -20,8 +20,12 @@
 
 namespace {
 
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarps = 8;                       // warps of ONE epilogue group (two per TMEM lane quadrant)
+// Two epilogue groups take alternate units: with one group the gate epilogue (tcgen05.ld -> gate -> bf16 -> swizzled smem,
+// ~1 500 busy clk per unit on 8 warps) was slower than the unit's MMAs (~1 200 clk), and the MMA thread waited for h
+// (tools/trace_mlp.py, profiles/r2_trace_mlp_roles.txt).
+constexpr int kEpiGroups = 2;
+constexpr int kThreads = 64 + 32 * kEpiWarps * kEpiGroups;
 
 // RES (C = 128 pairs, one plan for the batch): the three experts' Wab / Wc tiles stay RESIDENT in shared memory for all
 // tiles of the CTA (loaded once, before the previous kernel has finished) instead of streaming through the rings per
@@ -134,6 +138,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   float* sb_c = sb_ab + 5 * 2 * C;                                                                // [2][C]: this / the next tile's sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-role cycle accounting (compiled in with -DLDMB_MLP_TRACE only; read by tools/trace_mlp.py through ldmb_debug_tc_trace)
+#ifdef LDMB_MLP_TRACE
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+  auto lap = [&](int slot) { if (trace != nullptr) { const long long now = clock64(); tacc[slot] += now - tlast; tlast = now; } };
+#else
+  auto lap = [](int) {};
+#endif
   if (threadIdx.x == 0) trace_stamp(trace, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A1_BUFS; ++i) { ptx::mbar_init(&a1_full[i], 1); ptx::mbar_init(&a1_empty[i], 1); }
@@ -271,14 +283,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       bool ok = true;
       bool first_tile = true;
       for (int ti = next_active(0); ok && ti < my_tiles; ti = next_active(ti + 1)) {
+        lap(0);
         if (!wait_bar(&a1_full[ra.i], ra.ph, s_abort, fault, 24)) break;
+        lap(5);
         if (first_tile && issuer) trace_stamp(trace, 3);
         ptx::tc_fence_after();
         const uint64_t a1_desc = ptx::smem_desc_sw128(ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES));
         for (int s = 0; ok && s < UNITS + LAG; ++s) {
           if (s < UNITS) {
+            lap(0);
             if (!wait_bar(&d1_empty[rd1.i], rd1.ph ^ 1, s_abort, fault, 25)) { ok = false; break; }
+            lap(1);
             if (!wait_bar(&w1_full[r1.i], RES ? 0u : r1.ph, s_abort, fault, 26)) { ok = false; break; }   // RES: landed once, stays
+            lap(2);
             ptx::tc_fence_after();
             const uint32_t d1 = tmem_base + rd1.i * 128;
             const uint64_t b1_desc = ptx::smem_desc_sw128(ptx::smem_u32(w1 + r1.i * Cfg::W1_BYTES));
@@ -297,11 +314,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (s >= LAG) {
             const int u = s - LAG;
             if (u == 0) {
+              lap(0);
               if (!wait_bar(d2_empty, rd2.ph ^ 1, s_abort, fault, 27)) { ok = false; break; }
+              lap(6);
             }
+            lap(0);
             if (!wait_bar(&h_full[r2.i], r2.ph, s_abort, fault, 28)) { ok = false; break; }
+            lap(3);
             const uint32_t w2i = RES ? (uint32_t)u : r2.i;
             if (!wait_bar(&w2_full[w2i], RES ? 0u : r2.ph, s_abort, fault, 29)) { ok = false; break; }
+            lap(4);
             ptx::tc_fence_after();
             const uint64_t h_desc = ptx::smem_desc_sw128(ptx::smem_u32(hs + r2.i * Cfg::H_BYTES));
             const uint64_t b2_desc = ptx::smem_desc_sw128(ptx::smem_u32(w2 + w2i * Cfg::W2_BYTES));
@@ -321,16 +343,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         first_tile = false;
       }
       if (issuer) trace_stamp(trace, 5);
+#ifdef LDMB_MLP_TRACE
+      lap(0);
+      if (trace != nullptr && lane == 0) for (int i = 0; i < 7; ++i) trace[blockIdx.x * 16 + 16 * 256 + i] = tacc[i];
+#endif
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue warps: TMEM lane quadrant q, column half chalf
-    const int q = warp & 3, ew = warp - 2, chalf = ew >> 2;
+    // ===================================================== epilogue warps: group = units of that parity; TMEM lane quadrant q, column half chalf
+    const int grp = (warp - 2) >> 3, ew = (warp - 2) & 7, q = warp & 3, chalf = ew >> 2;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    uint8_t* slab = hs + ew * Cfg::SLAB_BYTES;              // epilogue-2 staging: the h ring is idle between tiles
+    uint8_t* slab = hs + ew * Cfg::SLAB_BYTES;              // epilogue-2 staging (group 0): the h ring is idle between tiles
     auto arrive = [&](uint64_t* bar) { if (CG == 2) ptx::mbar_arrive_leader(bar); else ptx::mbar_arrive(bar); };
-    Ring re1, rh, rd1, rd2;
+    Ring rd2;
     bool ok = true;
     int ta = 0;
     for (int ti = next_active(0); ok && ti < my_tiles; ++ta) {
@@ -340,89 +366,104 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (ti_next < my_tiles && (int)threadIdx.x - 64 < C)      // the next tile's c biases: visible after this tile's closing barrier
         sb_c[((ta + 1) & 1) * C + threadIdx.x - 64] = c_bias_sum(tile_word(ti_next), threadIdx.x - 64);
       const float* sbc = sb_c + (ta & 1) * C;
-      for (int u = 0; u < UNITS; ++u) {
+      for (int u = grp; u < UNITS; u += kEpiGroups) {
+        const int gu = ta * UNITS + u;                        // unit counter over this CTA's active tiles: ring positions follow from it
+        const uint32_t i1 = gu % W1S, p1 = (gu / W1S) & 1, ih = gu % HS, ph = (gu / HS) & 1, id = gu % ND1;
         const int e = u / NKB, slot = e == 0 ? 0 : 1 + ((word >> (8 * e)) & 0xff);   // row block of the stacked expert biases
         const float* sb = sb_ab + slot * 2 * C + (u % NKB) * 128;                     // [64 a-biases | 64 b-biases] of this unit
-        if (!wait_bar(&g1_done[re1.i], re1.ph, s_abort, fault, 30)) { ok = false; break; }
+        lap(0);
+        if (!wait_bar(&g1_done[i1], p1, s_abort, fault, 30)) { ok = false; break; }
+        lap(1);
         if (threadIdx.x == 64 && ta == 0 && u == 0) trace_stamp(trace, 6);
-        if (!wait_bar(&g2_done[rh.i], rh.ph ^ 1, s_abort, fault, 31)) { ok = false; break; }   // h slot free
+        if (!wait_bar(&g2_done[ih], ph ^ 1, s_abort, fault, 31)) { ok = false; break; }   // h slot free
+        lap(2);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + lane_off + rd1.i * 128;
+        const uint32_t t_row = tmem_base + lane_off + id * 128;
         if (!(a.dbg & 1)) {
-          const int ch = chalf;                                // 32-column half of the unit's 64 h columns
-          uint32_t ra_[32], rb_[32];
-          ptx::tmem_ld_32x32(t_row + ch * 32, ra_);
-          ptx::tmem_ld_32x32(t_row + 64 + ch * 32, rb_);
-          ptx::tmem_ld_wait();
-          // gate: (a + bias_a) * relu(b + bias_b); biases as 16-byte shared loads, adds / multiply as packed f32x2
-          float v[32];
-          const float4* sa4 = reinterpret_cast<const float4*>(sb + ch * 32);
-          const float4* sb4 = reinterpret_cast<const float4*>(sb + 64 + ch * 32);
+          // row r = q*32 + lane of the [128 x 64] bf16 chunk, 16-byte pieces chalf*4 .. +4, 128B-swizzled (piece ^ (r & 7))
+          const uint32_t hrow = ptx::smem_u32(hs + ih * Cfg::H_BYTES) + (q * 32 + lane) * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 ba = sa4[i], bb = sb4[i];
-            float2 a01 = add2(make_float2(__uint_as_float(ra_[4 * i]), __uint_as_float(ra_[4 * i + 1])), make_float2(ba.x, ba.y));
-            float2 a23 = add2(make_float2(__uint_as_float(ra_[4 * i + 2]), __uint_as_float(ra_[4 * i + 3])), make_float2(ba.z, ba.w));
-            float2 g01 = add2(make_float2(__uint_as_float(rb_[4 * i]), __uint_as_float(rb_[4 * i + 1])), make_float2(bb.x, bb.y));
-            float2 g23 = add2(make_float2(__uint_as_float(rb_[4 * i + 2]), __uint_as_float(rb_[4 * i + 3])), make_float2(bb.z, bb.w));
-            g01.x = fmaxf(g01.x, 0.f); g01.y = fmaxf(g01.y, 0.f); g23.x = fmaxf(g23.x, 0.f); g23.y = fmaxf(g23.y, 0.f);
-            a01 = mul2(a01, g01); a23 = mul2(a23, g23);
-            v[4 * i] = a01.x; v[4 * i + 1] = a01.y; v[4 * i + 2] = a23.x; v[4 * i + 3] = a23.y;
+          for (int hh = 0; hh < 2; ++hh) {                      // 16 of this warp's 32 h columns at a time (register budget of 576 threads)
+            const int c0 = chalf * 32 + hh * 16;
+            uint32_t ra_[16], rb_[16];
+            ptx::tmem_ld_32x16(t_row + c0, ra_);
+            ptx::tmem_ld_32x16(t_row + 64 + c0, rb_);
+            ptx::tmem_ld_wait();
+            // gate: (a + bias_a) * relu(b + bias_b); biases as 16-byte shared loads, adds / multiply as packed f32x2
+            float v[16];
+            const float4* sa4 = reinterpret_cast<const float4*>(sb + c0);
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + 64 + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 ba = sa4[i], bb = sb4[i];
+              float2 a01 = add2(make_float2(__uint_as_float(ra_[4 * i]), __uint_as_float(ra_[4 * i + 1])), make_float2(ba.x, ba.y));
+              float2 a23 = add2(make_float2(__uint_as_float(ra_[4 * i + 2]), __uint_as_float(ra_[4 * i + 3])), make_float2(ba.z, ba.w));
+              float2 g01 = add2(make_float2(__uint_as_float(rb_[4 * i]), __uint_as_float(rb_[4 * i + 1])), make_float2(bb.x, bb.y));
+              float2 g23 = add2(make_float2(__uint_as_float(rb_[4 * i + 2]), __uint_as_float(rb_[4 * i + 3])), make_float2(bb.z, bb.w));
+              g01.x = fmaxf(g01.x, 0.f); g01.y = fmaxf(g01.y, 0.f); g23.x = fmaxf(g23.x, 0.f); g23.y = fmaxf(g23.y, 0.f);
+              a01 = mul2(a01, g01); a23 = mul2(a23, g23);
+              v[4 * i] = a01.x; v[4 * i + 1] = a01.y; v[4 * i + 2] = a23.x; v[4 * i + 3] = a23.y;
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+              ptx::st_shared_v4(hrow + (((chalf * 4 + hh * 2 + p) ^ sw) << 4), pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
+                                pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
           }
-          // row r = q*32 + lane of the [128 x 64] bf16 chunk, 16-byte pieces ch*4 .. +4, 128B-swizzled (piece ^ (r & 7))
-          const uint32_t hrow = ptx::smem_u32(hs + rh.i * Cfg::H_BYTES) + (q * 32 + lane) * 128;
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            ptx::st_shared_v4(hrow + (((ch * 4 + p) ^ sw) << 4), pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
-                              pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
         }
+        lap(3);
         ptx::fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) { arrive(&h_full[rh.i]); arrive(&d1_empty[rd1.i]); }
-        re1.next(W1S);
-        rh.next(HS);
-        rd1.next(ND1);
+        if (lane == 0) { arrive(&h_full[ih]); arrive(&d1_empty[id]); }
+        lap(4);
       }
       if (!ok) break;
-      // ---- epilogue 2: D2 + biases -> 32 fp32 columns per slab (h ring as staging) -> TMA reduce-add into x
-      if (!wait_bar(d2_full, rd2.ph, s_abort, fault, 32)) break;
-      ptx::tc_fence_after();
-      const uint32_t t_row2 = tmem_base + lane_off + Cfg::D2_COL;
-      const int orow = m0 + q * 32;
+      if (grp == 0) {
+        // ---- epilogue 2 (group 0): D2 + biases -> 32 fp32 columns per slab (h ring as staging) -> TMA reduce-add into x
+        lap(0);
+        if (!wait_bar(d2_full, rd2.ph, s_abort, fault, 32)) break;
+        lap(5);
+        ptx::tc_fence_after();
+        const uint32_t t_row2 = tmem_base + lane_off + Cfg::D2_COL;
+        const int orow = m0 + q * 32;
 #pragma unroll 1
-      for (int c0 = chalf * 32; c0 < C; c0 += 64) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row2 + c0, r);
-        ptx::tmem_ld_wait();
-        if (lane == 0) ptx::bulk_wait_read<0>();          // the reduce that last used this slab has read it
-        __syncwarp();
-        const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
+        for (int c0 = chalf * 32; c0 < C; c0 += 64) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row2 + c0, r);
+          ptx::tmem_ld_wait();
+          if (lane == 0) ptx::bulk_wait_read<0>();          // the reduce that last used this slab has read it
+          __syncwarp();
+          const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-          ptx::st_shared_v4(srow + ((p ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * p]) + sbc[c0 + 4 * p]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 1]) + sbc[c0 + 4 * p + 1]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 2]) + sbc[c0 + 4 * p + 2]),
-                            __float_as_uint(__uint_as_float(r[4 * p + 3]) + sbc[c0 + 4 * p + 3]));
-        ptx::fence_proxy_async();
+          for (int p = 0; p < 8; ++p)
+            ptx::st_shared_v4(srow + ((p ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * p]) + sbc[c0 + 4 * p]),
+                              __float_as_uint(__uint_as_float(r[4 * p + 1]) + sbc[c0 + 4 * p + 1]),
+                              __float_as_uint(__uint_as_float(r[4 * p + 2]) + sbc[c0 + 4 * p + 2]),
+                              __float_as_uint(__uint_as_float(r[4 * p + 3]) + sbc[c0 + 4 * p + 3]));
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(a.dbg & 8)) { ptx::tma_reduce_add_2d(&tmO, slab, c0, orow); ptx::bulk_commit(); }
+        }
+        ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0 && !(a.dbg & 8)) { ptx::tma_reduce_add_2d(&tmO, slab, c0, orow); ptx::bulk_commit(); }
+        if (lane == 0) {
+          arrive(d2_empty);
+          ptx::bulk_wait_read<0>();                           // staging (h ring) is re-used by the next tile's epilogue 1
+        }
+        rd2.next(1);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        arrive(d2_empty);
-        ptx::bulk_wait_read<0>();                           // staging (h ring) is re-used by the next tile's epilogue 1
-      }
-      // every warp's reduce has read its slab before ANY warp writes h rows again (slabs and h rows of different warps overlap)
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      rd2.next(1);
+      // every reduce has read its slab before ANY warp of either group writes h rows again (slabs alias the h ring)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps * kEpiGroups) : "memory");
+      lap(6);
       if (threadIdx.x == 64 && ta == 0) trace_stamp(trace, 7);
       ti = ti_next;
     }
     if (lane == 0) ptx::bulk_wait_read<0>();                  // smem read by the reduces; the writes complete with the grid
     __syncwarp();
     if (threadIdx.x == 64) trace_stamp(trace, 8);
+#ifdef LDMB_MLP_TRACE
+    if (trace != nullptr && (threadIdx.x == 64 || threadIdx.x == 64 + 32 * kEpiWarps)) for (int i = 0; i < 7; ++i) trace[blockIdx.x * 16 + 16 * 256 + 8 + i] = tacc[i];
+#endif
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -699,8 +699,8 @@ void tc_context_destroy(TcContext* ctx) {
 
 int tc_trace_enable(TcContext* ctx, int on) {
   if (on && !ctx->trace_dev) {
-    if (cudaMalloc(&ctx->trace_dev, sizeof(long long) * kTraceSlots * 256) != cudaSuccess) return -1;
-    cudaMemset(ctx->trace_dev, 0, sizeof(long long) * kTraceSlots * 256);
+    if (cudaMalloc(&ctx->trace_dev, sizeof(long long) * kTraceSlots * 512) != cudaSuccess) return -1;     // [256 CTAs][16] stamps + [256][16] per-role accounting
+    cudaMemset(ctx->trace_dev, 0, sizeof(long long) * kTraceSlots * 512);
   } else if (!on && ctx->trace_dev) {
     cudaFree(ctx->trace_dev);
     ctx->trace_dev = nullptr;
@@ -709,7 +709,7 @@ int tc_trace_enable(TcContext* ctx, int on) {
 }
 int tc_trace_read(TcContext* ctx, long long* host, int max_ctas) {
   if (!ctx->trace_dev) return -1;
-  const int n = max_ctas < 256 ? max_ctas : 256;
+  const int n = max_ctas < 512 ? max_ctas : 512;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   if (cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * kTraceSlots * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;

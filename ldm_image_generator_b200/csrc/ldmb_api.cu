@@ -101,7 +101,8 @@ struct UNetState {
   bool fork_conv = getenv("LDMB_NO_FORK") == nullptr;
   // where the forked conv runs in the two-GEMM blocks (C >= 512): 1 (default) = from the norm on, beside the a|b GEMM; 2 = beside
   // the c-projection only, capped to the SMs that GEMM's grid leaves idle -- measured 22 % SLOWER end to end (16 CTAs walk 32 tiles
-  // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt)
+  // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
+  // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
   int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 1;
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
@@ -715,7 +716,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
-                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c));
+                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn);
   if (fork && !u.side_stream) {
     CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
