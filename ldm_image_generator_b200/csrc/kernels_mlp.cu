@@ -294,7 +294,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             lap(0);
             if (!wait_bar(&d1_empty[rd1.i], rd1.ph ^ 1, s_abort, fault, 25)) { ok = false; break; }
             lap(1);
-            if (!wait_bar(&w1_full[r1.i], RES ? 0u : r1.ph, s_abort, fault, 26)) { ok = false; break; }   // RES: landed once, stays
+            if ((!RES || first_tile) && !wait_bar(&w1_full[r1.i], RES ? 0u : r1.ph, s_abort, fault, 26)) { ok = false; break; }   // RES: landed once, stays
+                                                                                                                                // (a try_wait on a completed barrier still costs ~90 clk)
             lap(2);
             ptx::tc_fence_after();
             const uint32_t d1 = tmem_base + rd1.i * 128;
@@ -322,7 +323,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (!wait_bar(&h_full[r2.i], r2.ph, s_abort, fault, 28)) { ok = false; break; }
             lap(3);
             const uint32_t w2i = RES ? (uint32_t)u : r2.i;
-            if (!wait_bar(&w2_full[w2i], RES ? 0u : r2.ph, s_abort, fault, 29)) { ok = false; break; }
+            if ((!RES || first_tile) && !wait_bar(&w2_full[w2i], RES ? 0u : r2.ph, s_abort, fault, 29)) { ok = false; break; }
             lap(4);
             ptx::tc_fence_after();
             const uint64_t h_desc = ptx::smem_desc_sw128(ptx::smem_u32(hs + r2.i * Cfg::H_BYTES));
