@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libldmb200.so")
+LIB_PATH = os.environ.get("LDMB_LIB_PATH") or os.path.join(HERE, "libldmb200.so")     # override: A/B runs against another build of the same ABI
 
 LDMB_MAX_LEVELS = 8
 BF16, FP32_VALIDATE = 0, 1

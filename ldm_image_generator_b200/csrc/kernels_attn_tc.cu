@@ -454,10 +454,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const bf16* 
 }  // namespace
 
 static const bool g_attn_tc = getenv("LDMB_ATTN_TC") == nullptr || atoi(getenv("LDMB_ATTN_TC")) != 0;   // debug: 0 = mma.sync kernel
+static const int g_attn_tc_min_hw = getenv("LDMB_ATTN_TC_MIN_HW") ? atoi(getenv("LDMB_ATTN_TC_MIN_HW")) : 0;   // experiment: tcgen05 only for feature maps of at least this many pixels
 
 bool window_attention_tc_supported(int B, int H, int W, int C, int head_dim, int win_h, int win_w, long long ldo) {
   const long long tokens = (long long)B * H * W;
-  return g_attn_tc && head_dim == kD && C % 64 == 0 && win_h >= 1 && win_h <= 6 && win_w >= 1 && win_w <= 8 && ldo % 8 == 0 &&
+  return g_attn_tc && H * W >= g_attn_tc_min_hw && head_dim == kD && C % 64 == 0 && win_h >= 1 && win_h <= 6 && win_w >= 1 && win_w <= 8 && ldo % 8 == 0 &&
          tokens < (1LL << 31);
 }
 
