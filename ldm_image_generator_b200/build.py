@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldmb200.so")
 BUILD = os.path.join(HERE, "build")
-SOURCES = ["ldmb_api.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_attn.cu", "kernels_attn_tc.cu", "kernels_gconv.cu", "kernels_normconv.cu", "kernels_mlp.cu"]
+SOURCES = ["ldmb_api.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_attn.cu", "kernels_attn_tc.cu", "kernels_gconv.cu", "kernels_normconv.cu", "kernels_mlp.cu", "kernels_ffn_cluster.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"] + os.environ.get("LDMB_EXTRA_NVCC_FLAGS", "").split()     # e.g. -DLDMB_MLP_TRACE for tools/trace_mlp.py
 

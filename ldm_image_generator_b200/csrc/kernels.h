@@ -49,6 +49,12 @@ cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, c
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
                              cudaStream_t st);
 bool mlp_fused_per_image_supported(int M, int C, int rows_per_image);
+// The same feed-forward at C = 512 (kernels_ffn_cluster.cu): clusters of four CTA pairs share a 256-row tile, every pair gates a
+// quarter of the hidden chunks and exchanges them with its peers through distributed shared memory, then accumulates its quarter
+// of the output columns.  One shared plan for the batch (no per-image decisions).
+bool ffn_cluster_supported(int M, int C);
+cudaError_t launch_ffn_cluster(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                               float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, cudaStream_t st);
 
 // Dense 3x3 conv with 64 input and 64 output channels through the same halo-patch kernel (VAE level at full resolution):
 // out bf16 [B,H,W,64] = act(conv(in) + bias) (+ res), act(v) = max(v,0) + slope*min(v,0); w [64][9*64] tap-major.

@@ -1485,7 +1485,13 @@ extern "C" int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, 
                               float* x, int M, int C, int e1, int e2, void* stream) {
   if (!h || !xm || !w_ab || !b_ab || !w_c || !b_c || !x || M < 1 || e1 < 0 || e1 >= kExperts || e2 < 0 || e2 >= kExperts)
     return LDMB_ERR_INVALID;
-  if (!h->bf16() || !mlp_fused_supported(M, C)) return fail(h, LDMB_ERR_UNSUPPORTED, "fused feed-forward: bf16 mode, C = 128 or 256");
+  if (h->bf16() && ffn_cluster_supported(M, C)) {        // C = 512: the 8-CTA-cluster kernel
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_ffn_cluster(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, st));
+    return LDMB_OK;
+  }
+  if (!h->bf16() || !mlp_fused_supported(M, C)) return fail(h, LDMB_ERR_UNSUPPORTED, "fused feed-forward: bf16 mode, C = 128, 256 or 512");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, nullptr, 0, st));

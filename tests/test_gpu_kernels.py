@@ -237,7 +237,8 @@ def test_normconv_fused_kernel(handles, B, H, W, C):
 
 
 @pytest.mark.parametrize("M,C,e1,e2", [(256, 128, 0, 1), (4096, 128, 3, 2), (1000, 128, 1, 3), (65536, 128, 2, 0), (512, 256, 0, 3),
-                                       (16384, 256, 3, 1), (700, 256, 2, 1)])
+                                       (16384, 256, 3, 1), (700, 256, 2, 1),
+                                       (256, 512, 0, 1), (4096, 512, 1, 2), (700, 512, 3, 0), (8192, 512, 2, 3)])     # C = 512: the 8-CTA-cluster kernel
 def test_mlp_fused_kernel(handles, M, C, e1, e2):
     """Fused ReGLU feed-forward (general + 2 picked experts) vs fp64 torch on the same bf16-rounded operands."""
     h = handles["bf16"]

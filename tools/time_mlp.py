@@ -7,7 +7,7 @@ from ldm_image_generator_b200 import runtime
 from tools.bench_kernels import timeit
 
 h = runtime.Handle(torch.device("cuda", 0), "bf16")
-for lvl in (0, 1):
+for lvl in (0, 1, 2):
     Cc, M = 128 << lvl, 65536 >> (2 * lvl)
     xm = [torch.randn(M, Cc, device="cuda").bfloat16() for _ in range(3)]
     x = [torch.randn(M, Cc, device="cuda") for _ in range(3)]
