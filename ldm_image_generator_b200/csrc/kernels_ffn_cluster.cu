@@ -59,7 +59,7 @@ struct FfnArgs {
   int M;
   int dbg;                              // debug: 1 = gate epilogue writes nothing, 2 = no GEMM2 MMAs, 4 = no GEMM1 MMAs, 8 = no x update, 16 = no h copies to the peers
   int nsteps;                           // debug: run only the first nsteps of the schedule (NSTEPS = all)
-  int* progress;                        // debug: host-mapped [grid][16] last progress mark per warp (survives a launch failure)
+  int* progress;                        // debug: [grid][64] %globaltimer stamps (leader MMA warp: start of step s at [s]; epilogue warp 2: [32 + 4c + k])
   signed char sched[NSTEPS + 2];        // the MMA warp's static order: v >= 0: GEMM1 of this pair's chunk v; v < 0: GEMM2 of chunk -v-1
 };
 
@@ -81,7 +81,7 @@ __device__ __forceinline__ bool try_wait_cluster(uint64_t* bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
@@ -106,10 +106,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void arrive_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
 // bulk copy of this CTA's shared memory into another CTA of the cluster; the bytes complete on an mbarrier of the destination CTA
 __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
@@ -130,7 +130,9 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int slot) {
   }
 }
 
-#define MARK(code) do { if (a.progress != nullptr && lane == 0) { a.progress[blockIdx.x * 16 + warp] = (code); __threadfence_system(); } } while (0)
+
+// debug timeline: low 32 bits of %globaltimer into progress[cta][64] (device memory; LDMB_FFN_PROGRESS = its address)
+#define STAMP(idx) do { if (a.progress != nullptr && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.progress[blockIdx.x * 64 + (idx)] = (int)(unsigned)t_; } } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWab,
@@ -253,6 +255,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       bool first_g1 = true, first_g2 = true;
       for (int s = 0; ok && s < nsteps; ++s) {
         const int v = a.sched[s];
+        STAMP(s);
         if (v >= 0) {
           const int c = v, id = c % ND1;
           if (c >= ND1 && !wait_bar(&d1_empty[id], ((c / ND1) - 1) & 1, s_abort, fault, 42)) { ok = false; break; }
@@ -276,13 +279,9 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         } else {
           const int u = -v - 1, ih = u % HS;
           const uint32_t par = (u / HS) & 1;
-          MARK(1000 + u * 10 + 0);
           if (!wait_bar(&h_full[ih], par, s_abort, fault, 45)) { ok = false; break; }
-          MARK(1000 + u * 10 + 1);
           if (!wait_bar_cluster(&h_peer[ih], par, s_abort, fault, 46)) { ok = false; break; }
-          MARK(1000 + u * 10 + 2);
           if (!wait_bar(&w_full[stage], phase, s_abort, fault, 47)) { ok = false; break; }
-          MARK(1000 + u * 10 + 3);
           ptx::tc_fence_after();
           const uint64_t h_desc = ptx::smem_desc_sw128(ptx::smem_u32(hs + ih * H_BYTES));
           const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(wr + stage * W_BYTES));
@@ -291,16 +290,14 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             for (int k = 0; k < 4; ++k) mma(d2, h_desc + 2 * k, b_desc + 2 * k, (!first_g2 || k != 0) ? 1u : 0u);
           }
           first_g2 = false;
-          MARK(1000 + u * 10 + 4);
           commit(&w_empty[stage], pair_mask);
-          MARK(1000 + u * 10 + 5);
           // consumed here: one of the four arrivals the pair that gates the slot's NEXT chunk (u + HS) waits for.  (Signalling only that
           // pair keeps every h_free phase observed by its waiter -- a parity wait that skips phases passes vacuously.)
           if (!(a.dbg & 32) && u + HS < NU) commit(&h_free[ih], static_cast<uint16_t>(3u << (2 * ((u + HS) % NP))));
-          MARK(1000 + u * 10 + 6);
           if (++stage == WS) { stage = 0; phase ^= 1; }
         }
       }
+      STAMP(NSTEPS);
       if (ok && nsteps == NSTEPS) commit(d2_full, pair_mask);
       if (issuer) trace_stamp(trace, 5);
     } else {
@@ -308,19 +305,14 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int s = 0; ok && s < nsteps; ++s) {
         const int v = a.sched[s];
         if (v >= 0 || (a.dbg & 256)) continue;
+        STAMP(s);
         const int u = -v - 1, ih = u % HS;
-        MARK(2000 + u * 10);
         if (!(a.dbg & 2048) && !wait_bar(&h_full[ih], (u / HS) & 1, s_abort, fault, 48)) { ok = false; break; }
-        MARK(2000 + u * 10 + 1);
-        if (a.progress != nullptr && lane == 0) { a.progress[blockIdx.x * 16 + 10] = u; __threadfence_system(); }
         if (issuer && !(a.dbg & 64)) arrive_remote(mapa(ptx::smem_u32(&h_peer[ih]), crank & ~1u));
         __syncwarp();
-        MARK(2000 + u * 10 + 2);
       }
     }
     __syncwarp();
-    MARK(2999);
-    if (a.progress != nullptr && lane == 0) { a.progress[blockIdx.x * 16 + 11] = *s_abort; a.progress[blockIdx.x * 16 + 12] = ok ? 1 : 0; a.progress[blockIdx.x * 16 + 13] = nsteps; __threadfence_system(); }
   } else {
     // ===================================================== epilogue warps: TMEM lane quadrant q, column half chalf
     const int ew = warp - 2, q = warp & 3, chalf = ew >> 2;
@@ -330,13 +322,12 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     for (int c = 0; ok && c < n_gate; ++c) {
       const int u = NP * c + (int)pr, e = u / NKB, jj = u % NKB, id = c % ND1, ih = u % HS;
       const float* bp = a.b_ab + slot_of(e) * 2 * C + jj * 128;        // [64 a-biases | 64 b-biases] of this chunk
-      MARK(3000 + c * 10);
       if (!wait_bar(&d1_full[id], (c / ND1) & 1, s_abort, fault, 50)) { ok = false; break; }
-      MARK(3000 + c * 10 + 1);
       if (threadIdx.x == 64 && c == 0) trace_stamp(trace, 6);
+      if (ew == 0) STAMP(32 + 4 * c);
       // slot free: the chunk HS before this one has been consumed by all four pairs (this pair's n-th wait on the slot: c and c - 3 share it)
       if (u >= HS && !wait_bar_cluster(&h_free[ih], (c >= HS && NP * (c - HS) + (int)pr >= HS) ? 1u : 0u, s_abort, fault, 51)) { ok = false; break; }
-      MARK(3000 + c * 10 + 2);
+      if (ew == 0) STAMP(32 + 4 * c + 1);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + lane_off + id * 128;
       if (!(a.dbg & 1)) {
@@ -371,9 +362,9 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       __syncwarp();
       // (h_written before d1_empty: a warp can only be ND1 chunks ahead of another one's d1_empty arrival, so the ND1 barriers never alias)
       if (lane == 0) { ptx::mbar_arrive(&h_written[id]); ptx::mbar_arrive_leader(&d1_empty[id]); }
-      MARK(3000 + c * 10 + 3);
       if (ew != 0) continue;
       if (!wait_bar(&h_written[id], (c / ND1) & 1, s_abort, fault, 53)) { ok = false; break; }     // the whole chunk is written
+      STAMP(32 + 4 * c + 2);
       if (threadIdx.x == 64) {
         ptx::mbar_arrive(&h_full[ih]);
         if (!(a.dbg & 16)) {                                          // local consumer (MMA / relay warp of this CTA)
@@ -389,7 +380,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
       }
       __syncwarp();
-      MARK(3000 + c * 10 + 5);
+      STAMP(32 + 4 * c + 3);
     }
     if (ok && nsteps == NSTEPS) {
       // ---- epilogue 2: D2 + biases -> 32 fp32 columns per slab (the xm region is idle once every MMA has completed) -> TMA reduce-add
