@@ -42,11 +42,34 @@ struct TcTiling {
                         // 4 = staged epilogue without its TMA stores / reduces, 8 = no per-tile bias staging + CTA barrier
   int splits, kb_per;   // split-K (EPI_ACCUM_F32 through TMA reduce-add only): tile t covers k-blocks [sp*kb_per, ...)
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
+  int ast_ppm, ast_tpp;       // A-stationary mode: CTA pairs per m-tile, consecutive n-tiles per pair
 };
 
 // CG = CTAs per tile: 1 (128 x BN per CTA) or 2 (a CTA pair computes 256 x BN with cta_group::2; each CTA stages its
 // own 128 rows of A and BN/2 rows of B, so the pair moves 2/3 of the L2->SM bytes per FLOP of two independent CTAs).
-template <int BN, int CG> struct TcCfg {
+// AST (A-stationary; K <= 512, CTA pairs, 256-wide tiles): a pair keeps its 256 x K block of A resident in shared memory for
+// several consecutive n-tiles and streams only B through the ring -- the main loop of these GEMMs is bound by the bytes an SM
+// ingests from L2 (A 16 KB + B 16 KB per k-block otherwise), not by the tensor pipe.
+constexpr int kAstMaxKb = 8;
+template <int BN, int CG, bool AST = false> struct TcCfg;
+template <int BN, int CG> struct TcCfg<BN, CG, true> {
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = B_BYTES;                // the ring holds B tiles only
+  static constexpr int A_RES_BYTES = kAstMaxKb * A_BYTES;    // resident A: up to 8 k-block tiles of [128 x 128 B]
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SLAB_BYTES = 32 * 128;
+  static constexpr int SLABS = 1;                            // one staging slab per epilogue warp (bf16 epilogues: one slab per tile and warp)
+  static constexpr int STAGING_BYTES = kEpiWarps * SLABS * SLAB_BYTES;
+  static constexpr int FIXED_BYTES = 1024 + A_RES_BYTES + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
+  static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = FIXED_BYTES + STAGES * STAGE_BYTES;
+  static_assert(STAGES >= 3, "B ring");
+};
+template <int BN, int CG> struct TcCfg<BN, CG, false> {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -55,7 +78,9 @@ template <int BN, int CG> struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLAB_BYTES = 32 * 128;               // one warp's 32 rows x 128 B
-  static constexpr int STAGING_BYTES = kEpiWarps * 2 * SLAB_BYTES;   // per epilogue warp, double buffered
+  static constexpr int SLABS = 2;
+  static constexpr int A_RES_BYTES = 0;
+  static constexpr int STAGING_BYTES = kEpiWarps * SLABS * SLAB_BYTES;   // per epilogue warp, double buffered
   static constexpr int FIXED_BYTES = 1024 + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
   static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;       // 227 KB of dynamic smem per CTA
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -89,23 +114,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int AMODE, int CG>
+template <int BN, int AMODE, int CG, bool AST>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmDesc d, const TcTiling tl, int* fault, long long* trace) {
-  using Cfg = TcCfg<BN, CG>;
+  using Cfg = TcCfg<BN, CG, AST>;
   constexpr int STAGES_MAX = Cfg::STAGES;
   const int STAGES = tl.max_stages > 0 && tl.max_stages < STAGES_MAX ? tl.max_stages : STAGES_MAX;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;   // position in the CTA pair
   const bool leader = rank == 0;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_res = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));   // AST: resident A k-block tiles
+  uint8_t* tiles = a_res + Cfg::A_RES_BYTES;
   uint8_t* staging = tiles + STAGES_MAX * Cfg::STAGE_BYTES;      // 1024-aligned (every stage is a multiple of 1024 B)
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty = full + STAGES_MAX;
   uint64_t* tfull = empty + STAGES_MAX;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_full = tempty + 2;                                 // [kAstMaxKb] (AST)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + kAstMaxKb);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);
 
@@ -115,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kEpiWarps * CG); }
+    if (AST) for (int i = 0; i < kAstMaxKb; ++i) ptx::mbar_init(&a_full[i], 1);
     *s_abort = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
@@ -146,6 +174,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool sel_k = d.sel == 2 || d.sel == 3;        // weight rows selected per K slot
   auto srow = [&](int q) { return d.sel == 3 ? q * d.sel_stride : (q == 0 ? srow0 : (q == 1 ? srow1 : (q == 2 ? srow2 : srow3))); };
   const int total_tiles = skip_block ? 0 : tl.total;
+  // this CTA (pair)'s tiles: t_first + i * t_step, i < t_count.  Default: strided over the persistent grid.  AST: pair p owns ast_tpp
+  // consecutive n-tiles of m-tile p / ast_ppm.
+  int t_first = blockIdx.x / CG, t_step = gridDim.x / CG, t_count = total_tiles > t_first ? (total_tiles - t_first + t_step - 1) / t_step : 0;
+  if (AST) {
+    const int pair = blockIdx.x / CG, mt = pair / tl.ast_ppm, nt0 = (pair % tl.ast_ppm) * tl.ast_tpp;
+    t_first = mt * tl.n_tiles + nt0; t_step = 1;
+    t_count = (skip_block || mt >= tl.m_tiles || nt0 >= tl.n_tiles) ? 0 : min(tl.ast_tpp, tl.n_tiles - nt0);
+  }
   const bool is_producer = warp == 0;          // the producer warp waits for the previous kernel only after its weight prefetch
   if (!is_producer) {
     pdl_wait();
@@ -167,13 +203,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // while the previous kernel is still draining; only the activation (A) loads wait for it.
       int pre = 0;
       {
-        const int t = blockIdx.x / CG;
-        if (t < total_tiles) {
+        const int t = t_first;
+        if (t_count > 0) {
           const int sp = t / tiles_per_split, ts = t % tiles_per_split;
           const int z = ts / tiles_per_z, nt = (ts % tiles_per_z) % tl.n_tiles;
           const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
           for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
-            uint8_t* b_dst = tiles + pre * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+            uint8_t* b_dst = tiles + pre * Cfg::STAGE_BYTES + (AST ? 0 : Cfg::A_BYTES);
             int brow, bcol;
             b_coords(z, nt * BN, kb * BK, brow, bcol);
             if (issuer) {
@@ -187,8 +223,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       pdl_wait();
       if (issuer) trace_stamp(trace, 2);                         // previous kernel complete (producer's view)
+      if (AST && AMODE == AM_ROWS && t_count > 0 && issuer) {    // the pair's 256 x K block of A, once: one barrier per k-block so the MMAs start on the first
+        const int m0r = (t_first / tl.n_tiles) * (BM * CG) + (int)rank * BM;
+        for (int kb = 0; kb < tl.num_kb; ++kb) {
+          if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], Cfg::A_BYTES * CG);
+          if (CG == 2) ptx::tma_load_2d_2sm(a_res + kb * Cfg::A_BYTES, &tmA, &a_full[kb], kb * BK, m0r);
+          else ptx::tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, &a_full[kb], kb * BK, m0r);
+        }
+      }
+      __syncwarp();
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
+      for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
         const int sp = t / tiles_per_split, ts = t % tiles_per_split;
         const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
         const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
@@ -207,14 +252,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (b_done) --pre;
           else wait_bar(&empty[stage], phase ^ 1, s_abort, fault, 1);
           uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          uint8_t* b_dst = a_dst + (AST ? 0 : Cfg::A_BYTES);
           const int kk = kb * BK;
           int brow = 0, bcol = 0;
           if (!b_done) b_coords(z, n0, kk, brow, bcol);
           const int tap = AMODE == AM_CONV3 ? kk / d.cC : 0, c0 = AMODE == AM_CONV3 ? kk % d.cC : 0;
           if (issuer) {
             if (leader && !b_done) ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES * CG);   // both CTAs' bytes land on the leader's barrier
-            if (AMODE == AM_ROWS) {
+            if (AST) {
+              // A is resident
+            } else if (AMODE == AM_ROWS) {
               if (CG == 2) ptx::tma_load_2d_2sm(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
               else ptx::tma_load_2d(a_dst, &tmA, &full[stage], kk + (int)(z * d.a_koff_b), m0);
             } else {
@@ -225,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (CG == 2) ptx::tma_load_2d_2sm(b_dst, &tmB, &full[stage], bcol, brow);
               else ptx::tma_load_2d(b_dst, &tmB, &full[stage], bcol, brow);
             }
-            if (t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 3);   // first loads issued
+            if (ti == 0 && kb == kb0) trace_stamp(trace, 3);   // first loads issued
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -241,18 +288,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
+      for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const int kb0 = (t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (AST && ti == 0) wait_bar(&a_full[kb], 0, s_abort, fault, 5);
           wait_bar(&full[stage], phase, s_abort, fault, 3);
-          if (issuer && t == (int)(blockIdx.x / CG) && kb == kb0) trace_stamp(trace, 4);   // first operands landed
+          if (issuer && ti == 0 && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           // one descriptor per operand tile, k offsets added in 16-byte units (the MMA thread is issue-bound, see kernels_gconv.cu)
-          const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES));
-          const uint64_t b_desc = a_desc + Cfg::A_BYTES / 16;
+          const uint64_t s_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES));
+          const uint64_t a_desc = AST ? ptx::smem_desc_sw128(ptx::smem_u32(a_res + kb * Cfg::A_BYTES)) : s_desc;
+          const uint64_t b_desc = AST ? s_desc : s_desc + Cfg::A_BYTES / 16;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if ((tl.dbg & 2) || !issuer) continue;
@@ -283,13 +332,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
-    for (int t = blockIdx.x / CG; t < total_tiles; t += gridDim.x / CG) {
+    for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
       const int sp = t / tiles_per_split, ts = t % tiles_per_split;
       const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
       const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
-      if (!(tl.dbg & 8) || t == (int)(blockIdx.x / CG))
+      if (!(tl.dbg & 8) || ti == 0)
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
         float bv = 0.f;
@@ -301,9 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         sb[c] = bv;
       }
-      if (!(tl.dbg & 8) || t == (int)(blockIdx.x / CG)) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (!(tl.dbg & 8) || ti == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
-      if (threadIdx.x == 64) trace_stamp(trace, t == (int)(blockIdx.x / CG) ? 6 : 7);   // first / latest accumulator ready
+      if (threadIdx.x == 64) trace_stamp(trace, ti == 0 ? 6 : 7);   // first / latest accumulator ready
       ptx::tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < d.M;
@@ -319,8 +368,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
           for (int a0 = chalf * accw; a0 < BN; a0 += 2 * accw) {      // slabs interleaved between the two column warps
             if (n0 + a0 >= d.N) break;
-            uint8_t* slab = staging + (ew * 2 + slab_sel) * Cfg::SLAB_BYTES;
-            if (lane == 0) ptx::bulk_wait_read<1>();              // the store that last used this slab has read it
+            uint8_t* slab = staging + (ew * Cfg::SLABS + slab_sel % Cfg::SLABS) * Cfg::SLAB_BYTES;
+            if (lane == 0) { if (Cfg::SLABS == 1) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>(); }   // the store that last used this slab has read it
             __syncwarp();
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
 #pragma unroll
@@ -391,8 +440,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
           for (int a0 = chalf * 32; a0 < BN; a0 += 64) {
             if (n0 + a0 >= d.N) break;
-            uint8_t* slab = staging + (ew * 2 + slab_sel) * Cfg::SLAB_BYTES;
-            if (lane == 0) ptx::bulk_wait_read<1>();
+            uint8_t* slab = staging + (ew * Cfg::SLABS + slab_sel % Cfg::SLABS) * Cfg::SLAB_BYTES;
+            if (lane == 0) { if (Cfg::SLABS == 1) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>(); }
             __syncwarp();
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
             uint32_t r[32];
@@ -727,18 +776,19 @@ int tc_read_fault(TcContext* ctx, cudaStream_t s) {
   return v;
 }
 
-template <int BN, int AMODE, int CG>
+template <int BN, int AMODE, int CG, bool AST = false>
 static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                                   const GemmDesc& d, const TcTiling& tl, cudaStream_t s) {
-  using Cfg = TcCfg<BN, CG>;
+  using Cfg = TcCfg<BN, CG, AST>;
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, CG, AST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr.mark(ctx->device);
   }
   int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
-  if (tc_knobs().grid > 0 && tc_knobs().grid < grid) grid = (tc_knobs().grid / CG) * CG;   // debug
+  if (AST) grid = tl.m_tiles * tl.ast_ppm * CG;            // one pair per (m-tile, run of ast_tpp n-tiles)
+  if (!AST && tc_knobs().grid > 0 && tc_knobs().grid < grid) grid = (tc_knobs().grid / CG) * CG;   // debug
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
@@ -747,7 +797,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
   if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   if (CG == 2) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
   cfg.attrs = at; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMODE, CG>, tmA, tmB, tmO, d, tl, ctx->fault_dev, ctx->trace_dev);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, AMODE, CG, AST>, tmA, tmB, tmO, d, tl, ctx->fault_dev, ctx->trace_dev);
 }
 
 template <int AMODE, int CG>
@@ -771,6 +821,7 @@ const TcKnobs& tc_knobs() {
     t.mlp_dbg = geti("LDMB_MLP_DBG", 0);
     t.gconv_dbg = geti("LDMB_GCONV_DBG", 0);
     t.attn_dbg = geti("LDMB_ATTN_DBG", 0);
+    t.ast = geti("LDMB_TC_AST", 0);          // 1: A-stationary tiling for bf16-out K <= 512 GEMMs (measured slower: 17.7 vs 15.8 us at M4096 N3072 K512, see profiles/r2_experiment_a_stationary.txt)
     return t;
   }();
   return k;
@@ -807,6 +858,7 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
   tl.max_stages = tc_knobs().stages;
   tl.dbg = tc_knobs().dbg;
   tl.TW = tl.TH = tl.TB = 0;
+  tl.ast_ppm = tl.ast_tpp = 0;
 
   CUtensorMap tmA, tmB;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
@@ -902,11 +954,23 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
       tl.total *= tl.splits;
     }
   }
+  // A-stationary: bf16-out GEMMs with K <= 512 whose pairs would otherwise re-load the same A rows for every n-tile (ReGLU a|b at
+  // C = 512, in-projections): each pair takes ast_tpp consecutive n-tiles of one m-tile.  Same number of tile rounds as the strided
+  // persistent grid (ast_tpp = ceil(tiles / pairs)), fewer bytes per SM.
+  bool ast = false;
+  if (tc_knobs().ast && d.amode == AM_ROWS && cg == 2 && bn == 256 && batch == 1 && tl.splits == 1 && tl.tma_out &&
+      (d.epi == EPI_STORE || d.epi == EPI_REGLU) && tl.num_kb <= kAstMaxKb && d.a_koff_b == 0 && tl.n_tiles >= 2) {
+    const int pairs = ctx->num_sms / 2;
+    const int tpp = (tl.total + pairs - 1) / pairs;
+    const int ppm = (tl.n_tiles + tpp - 1) / tpp;
+    if (tpp >= 2 && tl.m_tiles * ppm <= pairs) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
+  }
   if (ctas_only != nullptr) {
-    const int grid = tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg;
+    const int grid = ast ? tl.m_tiles * tl.ast_ppm * cg : (tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg);
     *ctas_only = grid;
     return cudaSuccess;
   }
+  if (ast) return launch_tc_inst<256, AM_ROWS, 2, true>(ctx, tmA, tmB, tmO, d, tl, s);
   if (d.amode == AM_ROWS)
     return cg == 2 ? launch_tc_bn<AM_ROWS, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_ROWS, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);
   return cg == 2 ? launch_tc_bn<AM_CONV3, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_CONV3, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);
