@@ -48,6 +48,7 @@ struct GemmDesc {
   // grid.z batching (grouped convolution groups, per-block FiLM projections)
   int batch; long long a_koff_b, w_row_b, out_off_b, bias_off_b;
   int ctH, ctW, ctC;                   // EPI_CONVT: input height, width, output channels
+  int max_ctas;                        // > 0: cap of the persistent tcgen05 grid (SM partitioning: another kernel runs on the other SMs)
 };
 
 // Per-call parameters that change every step; kernels read them from device memory so the launch sequence is static.

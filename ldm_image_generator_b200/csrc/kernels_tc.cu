@@ -789,6 +789,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
   int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
   if (AST) grid = tl.m_tiles * tl.ast_ppm * CG;            // one pair per (m-tile, run of ast_tpp n-tiles)
   if (!AST && tc_knobs().grid > 0 && tc_knobs().grid < grid) grid = (tc_knobs().grid / CG) * CG;   // debug
+  if (!AST && d.max_ctas >= CG && d.max_ctas < grid) grid = (d.max_ctas / CG) * CG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
@@ -966,7 +967,8 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
     if (tpp >= 2 && tl.m_tiles * ppm <= pairs) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
   }
   if (ctas_only != nullptr) {
-    const int grid = ast ? tl.m_tiles * tl.ast_ppm * cg : (tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg);
+    int grid = ast ? tl.m_tiles * tl.ast_ppm * cg : (tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg);
+    if (!ast && d.max_ctas >= cg && d.max_ctas < grid) grid = (d.max_ctas / cg) * cg;
     *ctas_only = grid;
     return cudaSuccess;
   }

@@ -103,7 +103,8 @@ struct UNetState {
   // the c-projection only, capped to the SMs that GEMM's grid leaves idle -- measured 22 % SLOWER end to end (16 CTAs walk 32 tiles
   // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
   // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
-  int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 1;
+  int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 5;     // 5: SM-partitioned (run_block); 1: plain early fork; 2: late fork; 3 / 4: fork only the fused / two-GEMM blocks
+  int part_min_free = getenv("LDMB_PART_MIN_FREE") ? atoi(getenv("LDMB_PART_MIN_FREE")) : 48;   // fork mode 5: fewest SMs worth giving the conv
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
   size_t staging_slot_bytes = 0;
@@ -729,6 +730,19 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     conv_cap = tc_num_sms(h->tc) - tc_gemm_ctas(h->tc, c);
     if (conv_cap < C / 64) conv_cap = 0;                     // fewer idle SMs than channel slices: fork early instead
   }
+  // SM partitioning (fork mode 5, two-GEMM blocks): the a|b GEMM runs on just enough CTA pairs for its number of tile rounds (one
+  // round more where that would free fewer than ~1/3 of the SMs), the conv takes the SMs it leaves from the start of the block --
+  // forked beside a GEMM that fills the machine, the conv's CTAs only got SMs as the GEMM's persistent CTAs retired, i.e. the
+  // two ran back to back at the conv's own (latency-bound, 8 us) pace.
+  int ab_cap = 0, part_conv_cap = 0;
+  if (fork && !fused_ffn && u.fork_mode == 5) {
+    const int sms = tc_num_sms(h->tc), pairs = sms / 2;
+    const long long tiles = (long long)((M + 255) / 256) * ((6 * C + 255) / 256);
+    int rounds = (int)((tiles + pairs - 1) / pairs);
+    int need = (int)((tiles + rounds - 1) / rounds);
+    if (sms - 2 * need < u.part_min_free) { ++rounds; need = (int)((tiles + rounds - 1) / rounds); }
+    if (need < pairs && sms - 2 * need >= C / 64) { ab_cap = 2 * need; part_conv_cap = sms - 2 * need; }
+  }
   const bool late = conv_cap > 0;
   auto fork_conv_now = [&](int cap) -> int {
     CK(cudaEventRecord(u.ev_fork, st));
@@ -739,7 +753,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     return LDMB_OK;
   };
   if (fork && !late) {
-    if ((rc = fork_conv_now(0))) return rc;
+    if ((rc = fork_conv_now(part_conv_cap))) return rc;
   } else if (!fork && !fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
     GemmDesc d = gd();
@@ -764,6 +778,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.A = u.xm.p; d.lda = C; d.W = w.w_ab; d.ldw = C; d.bias = w.b_ab; d.out = u.hbuf.p; d.ldo = ldh;
     d.M = M; d.N = 6 * C; d.K = C; d.epi = EPI_REGLU; d.glu_chunk = glu_chunk_for(C);
     d.sel = 1; d.sel_span = 2 * C; d.sel_stride = 2 * C; d.plan = pl;
+    d.max_ctas = ab_cap;
     if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
     if (late && (rc = fork_conv_now(conv_cap))) return rc;
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
