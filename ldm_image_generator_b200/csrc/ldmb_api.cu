@@ -752,7 +752,10 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     CK(cudaEventRecord(u.ev_join, u.side_stream));
     return LDMB_OK;
   };
-  if (fork && !late) {
+  // attention blocks in partitioned mode: the in-projection GEMM and the attention core want the whole machine (a conv beside them
+  // stretched the core from 13 to 30 us), so the conv is forked after them, beside the a|b GEMM that leaves it its SMs
+  const bool fork_after_attn = fork && !late && w.attn && ab_cap > 0;
+  if (fork && !late && !fork_after_attn) {
     if ((rc = fork_conv_now(part_conv_cap))) return rc;
   } else if (!fork && !fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
   if (w.attn) {   // WindowAttention (attention.py:13-85): in_proj GEMM, per-window core; out_proj rides in the last GEMM
@@ -763,6 +766,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
     if ((rc = window_attention(h, u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, B, Hl, Wl, C, global ? Hl : kWindow,
                                global ? Wl : kWindow, global ? 0 : w.shift, pl, st, 0))) return rc;
+    if (fork_after_attn && (rc = fork_conv_now(part_conv_cap))) return rc;
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
   if (fused_ffn) {
