@@ -28,8 +28,9 @@ int tc_trace_read(TcContext* ctx, long long* host, int max_ctas);
 bool gconv_halo_supported(int B, int H, int W, int C);
 // max_ctas > 0 caps the persistent grid (rounded down to a whole number of channel slices): the conv then fits beside a GEMM
 // that leaves that many SMs idle
+// part / split_permille: 0 = the whole conv; 1 = only the first split_permille / 1000 of the spatial tiles, 2 = only the rest
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                              int C, const int* plan, cudaStream_t st, int max_ctas = 0);
+                              int C, const int* plan, cudaStream_t st, int max_ctas = 0, int part = 0, int split_permille = 0);
 // CTAs launch_gemm_tc puts on the machine for this GEMM (0: not a tcgen05 shape)
 int tc_gemm_ctas(TcContext* ctx, const GemmDesc& d);
 int tc_num_sms(const TcContext* ctx);
@@ -47,7 +48,7 @@ cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const i
 bool mlp_fused_supported(int M, int C);
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
-                             cudaStream_t st);
+                             cudaStream_t st, int max_ctas = 0);      // max_ctas > 0: cap of the persistent grid (SM partitioning)
 bool mlp_fused_per_image_supported(int M, int C, int rows_per_image);
 // The same feed-forward at C = 512 (kernels_ffn_cluster.cu): clusters of four CTA pairs share a 256-row tile, every pair gates a
 // quarter of the hidden chunks and exchanges them with its peers through distributed shared memory, then accumulates its quarter

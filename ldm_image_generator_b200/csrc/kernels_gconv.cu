@@ -37,6 +37,7 @@ struct GconvGeom {
   int out_rows, out_half, out_bytes;       // staged residual update: TB*TH*TW compact rows x 2 halves of 32 fp32 channels, each half
                                            // 1024-aligned (swizzle phase); out_bytes = 2 * out_half (0: red.global path)
   int dbg;                                 // debug experiments: 1 = no reds, 2 = one tap only
+  int sp_lo, sp_hi;                        // this launch covers the spatial tiles [sp_lo, sp_hi) of every channel slice (a conv split over two launches)
   // dense mode (VAE 3x3 conv with 64 input and 64 output channels, vae.py:57-58): out(bf16) = act(acc + bias) (+ res)
   int dense; float slope; bf16* out; const bf16* res;
 };
@@ -109,8 +110,8 @@ gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int nz = g.C / kSlice;
   const int z = blockIdx.x % nz;
   const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;
-  const int sp0 = blockIdx.x / nz, sp_step = gridDim.x / nz;
-  const int sp_end = skip_block ? 0 : n_sp;
+  const int sp0 = g.sp_lo + blockIdx.x / nz, sp_step = gridDim.x / nz;
+  const int sp_end = skip_block ? 0 : (g.sp_hi < n_sp ? g.sp_hi : n_sp);
 
   if (warp == 0) {
     if (lane == 0 && sp0 < sp_end) {
@@ -291,11 +292,11 @@ bool gconv_halo_supported(int B, int H, int W, int C) {
 // x fp32 [B,H,W,C] += conv3x3(xm bf16 [B,H,W,C], grouped by 32) + bias; w packed [C/64][64][9*64] block-diagonal pairs.
 static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
                                       int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res,
-                                      int max_ctas = 0);
+                                      int max_ctas = 0, int part = 0, int split_permille = 0);
 
 cudaError_t launch_gconv_halo(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
-                              int C, const int* plan, cudaStream_t st, int max_ctas) {
-  return launch_halo_common(ctx, xm, w, bias, x, B, H, W, C, plan, st, 0, 0.f, nullptr, nullptr, max_ctas);
+                              int C, const int* plan, cudaStream_t st, int max_ctas, int part, int split_permille) {
+  return launch_halo_common(ctx, xm, w, bias, x, B, H, W, C, plan, st, 0, 0.f, nullptr, nullptr, max_ctas, part, split_permille);
 }
 
 bool conv64_halo_supported(int C, int N) { return g_gconv_mode != 0 && C == kSlice && N == kSlice; }
@@ -310,7 +311,7 @@ cudaError_t launch_conv64_halo(TcContext* ctx, const void* in, const void* w, co
 
 static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void* w, const float* bias, float* x, int B, int H, int W,
                                       int C, const int* plan, cudaStream_t st, int dense, float slope, bf16* out, const bf16* res,
-                                      int max_ctas) {
+                                      int max_ctas, int part, int split_permille) {
   GconvGeom g;
   memset(&g, 0, sizeof(g));
   g.B = B; g.H = H; g.W = W; g.C = C;
@@ -383,7 +384,14 @@ static cudaError_t launch_halo_common(TcContext* ctx, const void* xm, const void
     attr.mark(ctx->device);
   }
   const int nz = C / kSlice;
-  const int n_sp = g.b_tiles * g.h_tiles * g.w_tiles;
+  const int n_sp_all = g.b_tiles * g.h_tiles * g.w_tiles;
+  // part 1 = the first split_permille / 1000 of the spatial tiles, part 2 = the rest (one conv as two launches: the first on the SMs a
+  // concurrent kernel leaves idle, the second on the whole machine)
+  const int sp_split = (int)((long long)n_sp_all * split_permille / 1000);
+  g.sp_lo = part == 2 ? sp_split : 0;
+  g.sp_hi = part == 1 ? sp_split : n_sp_all;
+  const int n_sp = g.sp_hi - g.sp_lo;
+  if (n_sp <= 0) return cudaSuccess;
   int per_z = ctx->num_sms / nz;
   if (max_ctas > 0 && max_ctas / nz < per_z) per_z = max_ctas / nz;
   if (per_z > n_sp) per_z = n_sp;

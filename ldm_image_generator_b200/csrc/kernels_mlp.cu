@@ -475,7 +475,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
 template <int C, int CG, bool RES>
 cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMap& tmWab, const CUtensorMap& tmWc, const CUtensorMap& tmO,
-                        const MlpArgs& a, cudaStream_t st) {
+                        const MlpArgs& a, cudaStream_t st, int max_ctas) {
   using Cfg = MlpCfg<C, CG, RES>;
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
@@ -484,6 +484,7 @@ cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMa
     attr.mark(ctx->device);
   }
   int grid = a.m_tiles * CG < ctx->num_sms ? a.m_tiles * CG : (ctx->num_sms / CG) * CG;
+  if (max_ctas >= CG && max_ctas < grid) grid = (max_ctas / CG) * CG;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
@@ -523,7 +524,7 @@ bool mlp_fused_per_image_supported(int M, int C, int rows_per_image) {
 // w_ab bf16 [5*2C, C] (per expert: a|b rows interleaved in chunks of 64), b_ab fp32 [5*2C]; w_c bf16 [>=5C, C], b_c fp32 [>=5C].
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
-                             cudaStream_t st) {
+                             cudaStream_t st, int max_ctas) {
   if (!mlp_fused_supported(M, C)) return cudaErrorNotSupported;
   if (plan_img != nullptr && !mlp_fused_per_image_supported(M, C, rows_per_image)) return cudaErrorNotSupported;
   const int cg = mlp_cta_group(M, C, plan_img != nullptr ? rows_per_image : 0);
@@ -547,7 +548,7 @@ cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, c
   if (!enc(&tmWc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_c, C, w_c_rows, 2, 64, C / cg)) return cudaErrorInvalidValue;
   if (!enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, C, M, 4, 32, 32)) return cudaErrorInvalidValue;
   static const bool resident = getenv("LDMB_MLP_RES") == nullptr || atoi(getenv("LDMB_MLP_RES")) != 0;
-  if (C == 128 && cg == 2 && plan_img == nullptr && resident) return launch_inst<128, 2, true>(ctx, tmX, tmWab, tmWc, tmO, a, st);
-  if (C == 128) return cg == 2 ? launch_inst<128, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st) : launch_inst<128, 1, false>(ctx, tmX, tmWab, tmWc, tmO, a, st);
-  return launch_inst<256, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st);
+  if (C == 128 && cg == 2 && plan_img == nullptr && resident) return launch_inst<128, 2, true>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
+  if (C == 128) return cg == 2 ? launch_inst<128, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas) : launch_inst<128, 1, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
+  return launch_inst<256, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
 }

@@ -104,6 +104,12 @@ struct UNetState {
   // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
   // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
   int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 5;     // 5: SM-partitioned (run_block); 1: plain early fork; 2: late fork; 3 / 4: fork only the fused / two-GEMM blocks
+  bool fork_fused = getenv("LDMB_FORK_FUSED") == nullptr || atoi(getenv("LDMB_FORK_FUSED")) != 0;   // fork the conv beside the fused feed-forward (C <= 256)
+  // fork mode 5, fused feed-forward blocks (C <= 256): the conv is split over two launches -- the first conv_split / 1000 of its tiles
+  // run on the split_free SMs the (capped) feed-forward kernel leaves, the rest on the whole machine afterwards.  0 = no split.
+  int conv_split128 = getenv("LDMB_CONV_SPLIT128") ? atoi(getenv("LDMB_CONV_SPLIT128")) : 0;     // measured slower (99.6 vs 98.9 ms per 50 steps at 220 / 260): off
+  int conv_split256 = getenv("LDMB_CONV_SPLIT256") ? atoi(getenv("LDMB_CONV_SPLIT256")) : 0;
+  int split_free = getenv("LDMB_SPLIT_FREE") ? atoi(getenv("LDMB_SPLIT_FREE")) : 20;
   int part_min_free = getenv("LDMB_PART_MIN_FREE") ? atoi(getenv("LDMB_PART_MIN_FREE")) : 48;   // fork mode 5: fewest SMs worth giving the conv
   // pinned staging ring for the per-call host tables
   char* staging = nullptr;
@@ -246,10 +252,11 @@ int window_attention(ldmb_handle* h, const void* qkv, const void* xm, const floa
 // x fp32 [B,H,W,C] += grouped conv3x3(xm) + bias (unet.py:30: groups of 32 channels).
 // tcgen05, halo-patch kernel (every activation read once) when C % 64 == 0, else the generic implicit-GEMM path.
 int grouped_conv(ldmb_handle* h, const void* xm, const void* w_g, const float* b_g, float* x, int B, int Hl, int Wl, int C,
-                 const int* pl, cudaStream_t st, bool force_generic, int max_ctas = 0) {
+                 const int* pl, cudaStream_t st, bool force_generic, int max_ctas = 0, int part = 0, int split_permille = 0) {
   const int M = B * Hl * Wl;
   if (h->bf16() && !h->force_simt && !force_generic && gconv_halo_supported(B, Hl, Wl, C)) {
-    CKLP(PK_GCONV, 2.0 * M * (double)C * 9 * kHeadDim, launch_gconv_halo(h->tc, xm, w_g, b_g, x, B, Hl, Wl, C, pl, st, max_ctas));
+    const double share = part == 1 ? split_permille / 1000.0 : (part == 2 ? 1.0 - split_permille / 1000.0 : 1.0);
+    CKLP(PK_GCONV, share * 2.0 * M * (double)C * 9 * kHeadDim, launch_gconv_halo(h->tc, xm, w_g, b_g, x, B, Hl, Wl, C, pl, st, max_ctas, part, split_permille));
     return LDMB_OK;
   }
   GemmDesc d = gd();
@@ -717,7 +724,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
-                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn);
+                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !u.fork_fused);
   if (fork && !u.side_stream) {
     CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
@@ -744,10 +751,13 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     if (need < pairs && sms - 2 * need >= C / 64) { ab_cap = 2 * need; part_conv_cap = sms - 2 * need; }
   }
   const bool late = conv_cap > 0;
+  // fused feed-forward blocks in partitioned mode: conv part 1 beside the capped feed-forward kernel, part 2 after the join
+  const int conv_split = (fork && fused_ffn && !w.attn && u.fork_mode == 5 && u.split_free >= C / 64) ? (C == 128 ? u.conv_split128 : u.conv_split256) : 0;
   auto fork_conv_now = [&](int cap) -> int {
     CK(cudaEventRecord(u.ev_fork, st));
     CK(cudaStreamWaitEvent(u.side_stream, u.ev_fork, 0));
-    int rc2 = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false, cap);
+    int rc2 = conv_split > 0 ? grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false, u.split_free, 1, conv_split)
+                             : grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, u.side_stream, false, cap);
     if (rc2) return rc2;
     CK(cudaEventRecord(u.ev_join, u.side_stream));
     return LDMB_OK;
@@ -772,9 +782,11 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   if (fused_ffn) {
     // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM
     CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
-         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st));
+         launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st,
+                          conv_split > 0 ? tc_num_sms(h->tc) - u.split_free : 0));
     if (w.attn && (rc = gemm(h, c, st, PK_FFN_C))) return rc;
     if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
+    if (conv_split > 0 && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false, 0, 2, conv_split))) return rc;
     return LDMB_OK;
   }
   {
