@@ -959,12 +959,13 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
   // C = 512, in-projections): each pair takes ast_tpp consecutive n-tiles of one m-tile.  Same number of tile rounds as the strided
   // persistent grid (ast_tpp = ceil(tiles / pairs)), fewer bytes per SM.
   bool ast = false;
-  if (tc_knobs().ast && d.amode == AM_ROWS && cg == 2 && bn == 256 && batch == 1 && tl.splits == 1 && tl.tma_out &&
+  if (tc_knobs().ast && d.amode == AM_ROWS && cg == 2 && (bn == 256 || bn == 128) && batch == 1 && tl.splits == 1 && tl.tma_out &&
       (d.epi == EPI_STORE || d.epi == EPI_REGLU) && tl.num_kb <= kAstMaxKb && d.a_koff_b == 0 && tl.n_tiles >= 2) {
     const int pairs = ctx->num_sms / 2;
-    const int tpp = (tl.total + pairs - 1) / pairs;
+    int tpp = (tl.total + pairs - 1) / pairs;
+    if (tpp > tl.n_tiles) tpp = tl.n_tiles;          // more m-tiles than pairs: one pair per m-tile (all its n-tiles), several waves of CTAs
     const int ppm = (tl.n_tiles + tpp - 1) / tpp;
-    if (tpp >= 2 && tl.m_tiles * ppm <= pairs) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
+    if (tpp >= 2 && (tl.m_tiles * ppm <= pairs || tc_knobs().ast >= 2)) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
   }
   if (ctas_only != nullptr) {
     int grid = ast ? tl.m_tiles * tl.ast_ppm * cg : (tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg);
@@ -972,7 +973,7 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
     *ctas_only = grid;
     return cudaSuccess;
   }
-  if (ast) return launch_tc_inst<256, AM_ROWS, 2, true>(ctx, tmA, tmB, tmO, d, tl, s);
+  if (ast) return bn == 256 ? launch_tc_inst<256, AM_ROWS, 2, true>(ctx, tmA, tmB, tmO, d, tl, s) : launch_tc_inst<128, AM_ROWS, 2, true>(ctx, tmA, tmB, tmO, d, tl, s);
   if (d.amode == AM_ROWS)
     return cg == 2 ? launch_tc_bn<AM_ROWS, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_ROWS, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);
   return cg == 2 ? launch_tc_bn<AM_CONV3, 2>(ctx, bn, tmA, tmB, tmO, d, tl, s) : launch_tc_bn<AM_CONV3, 1>(ctx, bn, tmA, tmB, tmO, d, tl, s);

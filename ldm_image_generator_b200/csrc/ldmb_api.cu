@@ -104,6 +104,7 @@ struct UNetState {
   // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
   // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
   int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 5;     // 5: SM-partitioned (run_block); 1: plain early fork; 2: late fork; 3 / 4: fork only the fused / two-GEMM blocks
+  int attn_fused_fork = getenv("LDMB_ATTN_FUSED_FORK") ? atoi(getenv("LDMB_ATTN_FUSED_FORK")) : 2;   // attention blocks at C <= 256: 0 = conv serial, 1 = forked at the start of the block, 2 = forked after the attention core
   bool fork_fused = getenv("LDMB_FORK_FUSED") == nullptr || atoi(getenv("LDMB_FORK_FUSED")) != 0;   // fork the conv beside the fused feed-forward (C <= 256)
   // fork mode 5, fused feed-forward blocks (C <= 256): the conv is split over two launches -- the first conv_split / 1000 of its tiles
   // run on the split_free SMs the (capped) feed-forward kernel leaves, the rest on the whole machine afterwards.  0 = no split.
@@ -724,7 +725,8 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
-                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !u.fork_fused);
+                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !u.fork_fused) &&
+                    !(fused_ffn && w.attn && u.attn_fused_fork == 0);
   if (fork && !u.side_stream) {
     CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&u.ev_fork, cudaEventDisableTiming));
@@ -764,7 +766,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   };
   // attention blocks in partitioned mode: the in-projection GEMM and the attention core want the whole machine (a conv beside them
   // stretched the core from 13 to 30 us), so the conv is forked after them, beside the a|b GEMM that leaves it its SMs
-  const bool fork_after_attn = fork && !late && w.attn && ab_cap > 0;
+  const bool fork_after_attn = fork && !late && w.attn && (ab_cap > 0 || (fused_ffn && u.attn_fused_fork == 2));
   if (fork && !late && !fork_after_attn) {
     if ((rc = fork_conv_now(part_conv_cap))) return rc;
   } else if (!fork && !fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
