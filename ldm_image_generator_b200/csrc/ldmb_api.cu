@@ -105,7 +105,7 @@ struct UNetState {
   // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
   int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 5;     // 5: SM-partitioned (run_block); 1: plain early fork; 2: late fork; 3 / 4: fork only the fused / two-GEMM blocks
   int attn_fused_fork = getenv("LDMB_ATTN_FUSED_FORK") ? atoi(getenv("LDMB_ATTN_FUSED_FORK")) : 2;   // attention blocks at C <= 256: 0 = conv serial, 1 = forked at the start of the block, 2 = forked after the attention core
-  bool fork_fused = getenv("LDMB_FORK_FUSED") == nullptr || atoi(getenv("LDMB_FORK_FUSED")) != 0;   // fork the conv beside the fused feed-forward (C <= 256)
+  int fork_fused = getenv("LDMB_FORK_FUSED") ? atoi(getenv("LDMB_FORK_FUSED")) : 3;   // fork the conv beside the fused feed-forward: bit 0 at C = 128, bit 1 at C = 256
   // fork mode 5, fused feed-forward blocks (C <= 256): the conv is split over two launches -- the first conv_split / 1000 of its tiles
   // run on the split_free SMs the (capped) feed-forward kernel leaves, the rest on the whole machine afterwards.  0 = no split.
   int conv_split128 = getenv("LDMB_CONV_SPLIT128") ? atoi(getenv("LDMB_CONV_SPLIT128")) : 0;     // measured slower (99.6 vs 98.9 ms per 50 steps at 220 / 260): off
@@ -725,7 +725,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
-                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !u.fork_fused) &&
+                    ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !((u.fork_fused >> (C == 128 ? 0 : 1)) & 1)) &&
                     !(fused_ffn && w.attn && u.attn_fused_fork == 0);
   if (fork && !u.side_stream) {
     CK(cudaStreamCreateWithFlags(&u.side_stream, cudaStreamNonBlocking));
