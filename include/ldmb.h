@@ -252,6 +252,12 @@ int ldmb_normconv(ldmb_handle* h, float* x, const float* film, void* xm, const v
 int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                    float* x, int M, int C, int e1, int e2, void* stream);
 
+/* The same kernel for an attention block (unet.py:44,47 + attention.py:82): additionally x += att . W_out^T + b_out, the MHA out_proj
+ * of the attention core's output att bf16 [M, C] (row stride ld_att elements), as extra K-chunks of the c-projection accumulator.
+ * w_c [6*C, C] / b_c [6*C]: rows 5C .. 6C are out_proj.weight / out_proj.bias.  C = 128 (M > 128) or 256. */
+int ldmb_mlp_fused_attn(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                        const void* att, int64_t ld_att, float* x, int M, int C, int e1, int e2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

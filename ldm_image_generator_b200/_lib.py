@@ -76,6 +76,7 @@ SIGNATURES = {
     "ldmb_channelnorm_film": (C.c_int, [_H, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ldmb_normconv": (C.c_int, [_H, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ldmb_mlp_fused": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "ldmb_mlp_fused_attn": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ldmb_grouped_conv3x3": (C.c_int, [_H, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ldmb_window_attention": (C.c_int, [_H, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _P]),

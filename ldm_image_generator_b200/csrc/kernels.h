@@ -48,7 +48,9 @@ cudaError_t launch_normconv(TcContext* ctx, float* x, const float* film, const i
 bool mlp_fused_supported(int M, int C);
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
-                             cudaStream_t st, int max_ctas = 0);      // max_ctas > 0: cap of the persistent grid (SM partitioning)
+                             cudaStream_t st, int max_ctas = 0,       // max_ctas > 0: cap of the persistent grid (SM partitioning)
+                             const void* att = nullptr, long long ld_att = 0);   // attention blocks: x += att . W_out^T (rows 5C .. 6C of w_c, bias b_c[5C ..]) in the same kernel
+bool mlp_fused_att_supported(int M, int C);
 bool mlp_fused_per_image_supported(int M, int C, int rows_per_image);
 // The same feed-forward at C = 512 (kernels_ffn_cluster.cu): clusters of four CTA pairs share a 256-row tile, every pair gates a
 // quarter of the hidden chunks and exchanges them with its peers through distributed shared memory, then accumulates its quarter

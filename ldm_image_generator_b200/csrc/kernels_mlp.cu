@@ -30,9 +30,13 @@ constexpr int kThreads = 64 + 32 * kEpiWarps * kEpiGroups;
 // RES (C = 128 pairs, one plan for the batch): the three experts' Wab / Wc tiles stay RESIDENT in shared memory for all
 // tiles of the CTA (loaded once, before the previous kernel has finished) instead of streaming through the rings per
 // tile -- at 4 tiles per CTA the re-streamed weights were 144 of the 176 KB a CTA ingests per tile.
-template <int C, int CG, bool RES> struct MlpCfg {
+// ATT (attention blocks): NKB extra GEMM2 units per tile whose A operand is the tile of the attention core's output (TMA-loaded into the
+// h ring) and whose weights are the MHA out_proj rows (slot 5 of w_c): x += att . W_out^T rides in the same D2 accumulator
+// (attention.py:82 out_proj; unet.py:44,47) -- no separate K = C GEMM and no second pass of reduce-adds over x.
+template <int C, int CG, bool RES, bool ATT = false> struct MlpCfg {
   static constexpr int NKB = C / 64;                       // k-blocks of GEMM1 = 64-column h chunks per expert
-  static constexpr int UNITS = 3 * NKB;
+  static constexpr int UNITS = 3 * NKB;                   // gated units (GEMM1 + gate + GEMM2)
+  static constexpr int UNITS2 = UNITS + (ATT ? NKB : 0);   // GEMM2 units
   static constexpr int A1_BYTES = NKB * 128 * 128;         // xm tile: NKB k-block tiles of [128 rows x 128 B]
   static constexpr int A1_BUFS = (C == 128 && CG == 2 && !RES) ? 2 : 1;
   // One W1 stage = all NKB k-block tiles of a unit's Wab rows, one W2 stage = the unit's Wc tile: a unit costs the MMA
@@ -49,6 +53,7 @@ template <int C, int CG, bool RES> struct MlpCfg {
   static constexpr int SLAB_BYTES = 32 * 128;              // epilogue-2 staging aliases the (then idle) h ring
   static constexpr int TILE_BYTES = A1_BUFS * A1_BYTES + W1S * W1_BYTES + W2S * W2_BYTES + HS * H_BYTES;
   static_assert(!RES || (C == 128 && CG == 2), "resident weights fit for C = 128 pairs only");
+  static_assert(!(RES && ATT), "the attention units stream their operands");
   static_assert(W1S <= 8 && W2S <= 8, "barrier slots");
   static constexpr int BAR_BYTES = 512;
   static constexpr int BIAS_FLOATS = 5 * 2 * C + 2 * C;    // a|b biases of all five experts + the tile's summed c biases (x2)
@@ -108,17 +113,22 @@ __device__ __forceinline__ void trace_stamp(long long* trace, int slot) {
   }
 }
 
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(ptx::smem_u32(bar)), "r"(n) : "memory");
+}
+
 struct Ring {
   uint32_t i = 0, ph = 0;
   __device__ __forceinline__ void next(uint32_t n) { if (++i == n) { i = 0; ph ^= 1; } }
 };
 
-template <int C, int CG, bool RES>
+template <int C, int CG, bool RES, bool ATT>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWab,
-                 const __grid_constant__ CUtensorMap tmWc, const __grid_constant__ CUtensorMap tmO, const MlpArgs a, int* fault, long long* trace) {
-  using Cfg = MlpCfg<C, CG, RES>;
-  constexpr int NKB = Cfg::NKB, UNITS = Cfg::UNITS, LAG = Cfg::LAG, ND1 = Cfg::ND1, W1S = Cfg::W1S, HS = Cfg::HS, W2S = Cfg::W2S;
+                 const __grid_constant__ CUtensorMap tmWc, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmAtt,
+                 const MlpArgs a, int* fault, long long* trace) {
+  using Cfg = MlpCfg<C, CG, RES, ATT>;
+  constexpr int NKB = Cfg::NKB, UNITS = Cfg::UNITS, UNITS2 = Cfg::UNITS2, LAG = Cfg::LAG, ND1 = Cfg::ND1, W1S = Cfg::W1S, HS = Cfg::HS, W2S = Cfg::W2S;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -157,6 +167,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     *s_abort = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmX); ptx::prefetch_tensormap(&tmWab); ptx::prefetch_tensormap(&tmWc); ptx::prefetch_tensormap(&tmO);
+    if (ATT) ptx::prefetch_tensormap(&tmAtt);
   }
   if (warp == 1) {
     if (CG == 2) { ptx::tmem_alloc_2sm(tmem_slot, 512); ptx::tmem_relinquish_2sm(); }
@@ -177,7 +188,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     return ti;
   };
   auto c_bias_sum = [&](int word, int i) -> float {          // general + e1 + e2 (modules.py:15)
-    return a.b_c[i] + a.b_c[(1 + ((word >> 8) & 0xff)) * C + i] + a.b_c[(1 + ((word >> 16) & 0xff)) * C + i];
+    return a.b_c[i] + a.b_c[(1 + ((word >> 8) & 0xff)) * C + i] + a.b_c[(1 + ((word >> 16) & 0xff)) * C + i] + (ATT ? a.b_c[5 * C + i] : 0.f);   // + out_proj bias
   };
   for (int i = threadIdx.x; i < 5 * 2 * C; i += kThreads) sb_ab[i] = a.b_ab[i];
   {
@@ -223,17 +234,26 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (++n1 % UNITS == 0) w1_ti = next_active(w1_ti + 1);
       };
       auto issue_w2 = [&]() {
-        const int u = n2 % UNITS, e = u / NKB, j = u % NKB;
+        const int u = n2 % UNITS2;
+        const bool att_unit = ATT && u >= UNITS;             // out_proj unit: weights = slot 5 of w_c, A operand = the attention output tile
+        const int e = u / NKB, j = att_unit ? u - UNITS : u % NKB;
         if (!RES && !wait_bar(&g2_done[r2.i], r2.ph ^ 1, s_abort, fault, 23)) { ok = false; return; }
-        const int row = slot_of(w2_ti, e) * C + (int)rank * Cfg::B2_ROWS;
+        const int row = (att_unit ? 5 : slot_of(w2_ti, e)) * C + (int)rank * Cfg::B2_ROWS;
         if (issuer) {
           if (leader) ptx::mbar_arrive_expect_tx(&w2_full[r2.i], Cfg::W2_BYTES * CG);
           if (CG == 2) ptx::tma_load_2d_2sm(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
           else ptx::tma_load_2d(w2 + r2.i * Cfg::W2_BYTES, &tmWc, &w2_full[r2.i], j * 64, row);
+          if (att_unit) {
+            // the h slot of this unit is filled by TMA instead of the gate epilogue: its barrier still counts the epilogue warps' arrivals
+            const int m0w = (t0 + w2_ti * t_step) * (128 * CG) + (int)rank * 128;
+            if (leader) { ptx::mbar_arrive_expect_tx(&h_full[r2.i], Cfg::H_BYTES * CG); mbar_arrive_n(&h_full[r2.i], kEpiWarps * CG - 1); }
+            if (CG == 2) ptx::tma_load_2d_2sm(hs + r2.i * Cfg::H_BYTES, &tmAtt, &h_full[r2.i], j * 64, m0w);
+            else ptx::tma_load_2d(hs + r2.i * Cfg::H_BYTES, &tmAtt, &h_full[r2.i], j * 64, m0w);
+          }
         }
         __syncwarp();
         r2.next(W2S);
-        if (++n2 % UNITS == 0) w2_ti = next_active(w2_ti + 1);
+        if (++n2 % UNITS2 == 0) w2_ti = next_active(w2_ti + 1);
       };
       // fill both weight rings while the previous kernel is still draining; only the xm tiles wait for it
       while (ok && w1_ti < my_tiles && n1 < W1S) issue_w1();
@@ -256,9 +276,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         __syncwarp();
         ra.next(Cfg::A1_BUFS);
-        for (int s = 0; !RES && ok && s < UNITS + LAG; ++s) {     // same order as the MMA thread consumes
+        for (int s = 0; !RES && ok && s < UNITS2 + LAG; ++s) {     // same order as the MMA thread consumes
           if (s < UNITS && ta * UNITS + s >= n1) issue_w1();
-          if (ok && s >= LAG && ta * UNITS + s - LAG >= n2) issue_w2();
+          if (ok && s >= LAG && ta * UNITS2 + s - LAG >= n2) issue_w2();
         }
       }
     }
@@ -289,7 +309,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (first_tile && issuer) trace_stamp(trace, 3);
         ptx::tc_fence_after();
         const uint64_t a1_desc = ptx::smem_desc_sw128(ptx::smem_u32(a1 + ra.i * Cfg::A1_BYTES));
-        for (int s = 0; ok && s < UNITS + LAG; ++s) {
+        for (int s = 0; ok && s < UNITS2 + LAG; ++s) {
           if (s < UNITS) {
             lap(0);
             if (!wait_bar(&d1_empty[rd1.i], rd1.ph ^ 1, s_abort, fault, 25)) { ok = false; break; }
@@ -368,8 +388,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         sb_c[((ta + 1) & 1) * C + threadIdx.x - 64] = c_bias_sum(tile_word(ti_next), threadIdx.x - 64);
       const float* sbc = sb_c + (ta & 1) * C;
       for (int u = grp; u < UNITS; u += kEpiGroups) {
-        const int gu = ta * UNITS + u;                        // unit counter over this CTA's active tiles: ring positions follow from it
-        const uint32_t i1 = gu % W1S, p1 = (gu / W1S) & 1, ih = gu % HS, ph = (gu / HS) & 1, id = gu % ND1;
+        const int gu = ta * UNITS + u, gu2 = ta * UNITS2 + u;  // gated-unit / GEMM2-unit counters over this CTA's active tiles: ring positions follow from them
+        const uint32_t i1 = gu % W1S, p1 = (gu / W1S) & 1, ih = gu2 % HS, ph = (gu2 / HS) & 1, id = gu % ND1;
         const int e = u / NKB, slot = e == 0 ? 0 : 1 + ((word >> (8 * e)) & 0xff);   // row block of the stacked expert biases
         const float* sb = sb_ab + slot * 2 * C + (u % NKB) * 128;                     // [64 a-biases | 64 b-biases] of this unit
         lap(0);
@@ -473,13 +493,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (threadIdx.x == 0) trace_stamp(trace, 9);
 }
 
-template <int C, int CG, bool RES>
+template <int C, int CG, bool RES, bool ATT = false>
 cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMap& tmWab, const CUtensorMap& tmWc, const CUtensorMap& tmO,
-                        const MlpArgs& a, cudaStream_t st, int max_ctas) {
-  using Cfg = MlpCfg<C, CG, RES>;
+                        const CUtensorMap& tmAtt, const MlpArgs& a, cudaStream_t st, int max_ctas) {
+  using Cfg = MlpCfg<C, CG, RES, ATT>;
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, CG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, CG, RES, ATT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr.mark(ctx->device);
   }
@@ -493,7 +513,7 @@ cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMa
   if (g_ldmb_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   if (CG == 2) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
   cfg.attrs = at; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, mlp_fused_kernel<C, CG, RES>, tmX, tmWab, tmWc, tmO, a, ctx->fault_dev, ctx->trace_dev);
+  return cudaLaunchKernelEx(&cfg, mlp_fused_kernel<C, CG, RES, ATT>, tmX, tmWab, tmWc, tmO, tmAtt, a, ctx->fault_dev, ctx->trace_dev);
 }
 
 }  // namespace
@@ -501,6 +521,10 @@ cudaError_t launch_inst(TcContext* ctx, const CUtensorMap& tmX, const CUtensorMa
 static int g_mlp_mode = getenv("LDMB_MLP_FUSED") ? atoi(getenv("LDMB_MLP_FUSED")) : 2;   // 0 off, 1 single CTA, 2 CTA pairs
 
 bool mlp_fused_supported(int M, int C) { return g_mlp_mode != 0 && (C == 128 || C == 256) && M >= 1; }
+
+static const bool g_mlp_att = getenv("LDMB_MLP_ATT") == nullptr || atoi(getenv("LDMB_MLP_ATT")) != 0;   // 0: out_proj as a separate K = C GEMM
+// the out_proj units need CTA pairs (the single-CTA variant covers a lone 128-row tile of C = 128 only)
+bool mlp_fused_att_supported(int M, int C) { return g_mlp_att && mlp_fused_supported(M, C) && g_mlp_mode == 2 && (M > 128 || C == 256); }
 
 // CTAs of a cluster: pairs, except where a lone 128-row tile (C = 128) or -- with per-image decisions -- an image of an odd
 // number of 128-row tiles needs the single-CTA variant (C = 128 only).  0 = this shape cannot run fused.
@@ -524,7 +548,7 @@ bool mlp_fused_per_image_supported(int M, int C, int rows_per_image) {
 // w_ab bf16 [5*2C, C] (per expert: a|b rows interleaved in chunks of 64), b_ab fp32 [5*2C]; w_c bf16 [>=5C, C], b_c fp32 [>=5C].
 cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
                              float* x, int M, int C, int w_c_rows, const int* plan, int e1, int e2, const int* plan_img, int rows_per_image,
-                             cudaStream_t st, int max_ctas) {
+                             cudaStream_t st, int max_ctas, const void* att, long long ld_att) {
   if (!mlp_fused_supported(M, C)) return cudaErrorNotSupported;
   if (plan_img != nullptr && !mlp_fused_per_image_supported(M, C, rows_per_image)) return cudaErrorNotSupported;
   const int cg = mlp_cta_group(M, C, plan_img != nullptr ? rows_per_image : 0);
@@ -547,8 +571,22 @@ cudaError_t launch_mlp_fused(TcContext* ctx, const void* xm, const void* w_ab, c
   if (!enc(&tmWab, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_ab, C, 5 * 2 * C, 2, 64, 128 / cg)) return cudaErrorInvalidValue;
   if (!enc(&tmWc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_c, C, w_c_rows, 2, 64, C / cg)) return cudaErrorInvalidValue;
   if (!enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, C, M, 4, 32, 32)) return cudaErrorInvalidValue;
+  CUtensorMap tmAtt;
+  memset(&tmAtt, 0, sizeof(tmAtt));
+  if (att != nullptr) {
+    // x += att . W_out^T in the same kernel (attention blocks): att bf16 [M, C] rows of stride ld_att, W_out = rows 5C .. 6C of w_c
+    if (!mlp_fused_att_supported(M, C) || plan_img != nullptr || w_c_rows < 6 * C || ld_att % 8 != 0) return cudaErrorNotSupported;
+    const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld_att * 2};
+    const cuuint32_t box[2] = {64, 128};
+    if (ctx->encode(&tmAtt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(att), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    if (C == 128) return launch_inst<128, 2, false, true>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas);
+    return launch_inst<256, 2, false, true>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas);
+  }
   static const bool resident = getenv("LDMB_MLP_RES") == nullptr || atoi(getenv("LDMB_MLP_RES")) != 0;
-  if (C == 128 && cg == 2 && plan_img == nullptr && resident) return launch_inst<128, 2, true>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
-  if (C == 128) return cg == 2 ? launch_inst<128, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas) : launch_inst<128, 1, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
-  return launch_inst<256, 2, false>(ctx, tmX, tmWab, tmWc, tmO, a, st, max_ctas);
+  if (C == 128 && cg == 2 && plan_img == nullptr && resident) return launch_inst<128, 2, true>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas);
+  if (C == 128) return cg == 2 ? launch_inst<128, 2, false>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas) : launch_inst<128, 1, false>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas);
+  return launch_inst<256, 2, false>(ctx, tmX, tmWab, tmWc, tmO, tmAtt, a, st, max_ctas);
 }

@@ -782,11 +782,12 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   }
   // RandomMoE of ReGLU experts (modules.py:14-15,34-36): general + e1 + e2, experts resolved on the device from the plan
   if (fused_ffn) {
-    // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM
+    // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM; in attention blocks the out_proj rides along
+    const bool att_in_mlp = w.attn && mlp_fused_att_supported(M, C);
     CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
          launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st,
-                          conv_split > 0 ? tc_num_sms(h->tc) - u.split_free : 0));
-    if (w.attn && (rc = gemm(h, c, st, PK_FFN_C))) return rc;
+                          conv_split > 0 ? tc_num_sms(h->tc) - u.split_free : 0, att_in_mlp ? toff(h, u.hbuf.p, 3LL * C) : nullptr, ldh));
+    if (w.attn && !att_in_mlp && (rc = gemm(h, c, st, PK_FFN_C))) return rc;
     if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
     if (conv_split > 0 && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false, 0, 2, conv_split))) return rc;
     return LDMB_OK;
@@ -1528,5 +1529,18 @@ extern "C" int ldmb_mlp_fused(ldmb_handle* h, const void* xm, const void* w_ab, 
   CK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C, launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 5 * C, nullptr, e1, e2, nullptr, 0, st));
+  return LDMB_OK;
+}
+
+extern "C" int ldmb_mlp_fused_attn(ldmb_handle* h, const void* xm, const void* w_ab, const float* b_ab, const void* w_c, const float* b_c,
+                                   const void* att, int64_t ld_att, float* x, int M, int C, int e1, int e2, void* stream) {
+  if (!h || !xm || !w_ab || !b_ab || !w_c || !b_c || !att || !x || M < 1 || e1 < 0 || e1 >= kExperts || e2 < 0 || e2 >= kExperts || ld_att < C)
+    return LDMB_ERR_INVALID;
+  if (!h->bf16() || !mlp_fused_att_supported(M, C))
+    return fail(h, LDMB_ERR_UNSUPPORTED, "fused feed-forward + out_proj: bf16 mode, C = 128 (more than one 128-row tile) or 256");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKLP(PK_FFN_AB, 2.0 * M * (double)C * 10 * C,
+       launch_mlp_fused(h->tc, xm, w_ab, b_ab, w_c, b_c, x, M, C, 6 * C, nullptr, e1, e2, nullptr, 0, st, 0, att, ld_att));
   return LDMB_OK;
 }

@@ -229,6 +229,10 @@ class Handle:
         self.check(self.lib.ldmb_mlp_fused(self.h, xm.data_ptr(), w_ab.data_ptr(), b_ab.data_ptr(), w_c.data_ptr(), b_c.data_ptr(),
                                            x.data_ptr(), M, Cc, e1, e2, stream_ptr(self.device)))
 
+    def mlp_fused_attn(self, xm, w_ab, b_ab, w_c, b_c, att, x, M, Cc, e1, e2) -> None:
+        self.check(self.lib.ldmb_mlp_fused_attn(self.h, xm.data_ptr(), w_ab.data_ptr(), b_ab.data_ptr(), w_c.data_ptr(), b_c.data_ptr(),
+                                                att.data_ptr(), att.stride(-2), x.data_ptr(), M, Cc, e1, e2, stream_ptr(self.device)))
+
     def normconv(self, x, film, xm, w_packed, bias, B, H, W, Cc) -> None:
         self.check(self.lib.ldmb_normconv(self.h, x.data_ptr(), film.data_ptr(), xm.data_ptr(), w_packed.data_ptr(), bias.data_ptr(),
                                           B, H, W, Cc, stream_ptr(self.device)))

@@ -261,3 +261,32 @@ def test_mlp_fused_kernel(handles, M, C, e1, e2):
         ref += hh.bfloat16().double() @ wc[e].double().t() + bc[e].double()       # h is rounded to bf16 between the two GEMMs
     assert h.device_fault() == 0
     assert _rel(x - x0, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,C,e1,e2", [(256, 128, 0, 1), (65536, 128, 2, 3), (1000, 128, 3, 1), (512, 256, 1, 0), (16384, 256, 2, 3), (700, 256, 0, 2)])
+def test_mlp_fused_with_out_proj(handles, M, C, e1, e2):
+    """Attention blocks: the fused feed-forward kernel also adds the MHA out_proj of the attention output (extra K-chunks of the
+    c-projection accumulator) -- vs fp64 torch on the same bf16-rounded operands; att is a strided view like the step's hbuf."""
+    h = handles["bf16"]
+    g = torch.Generator(device="cuda").manual_seed(M + C + e1 * 5 + e2 + 17)
+    xm = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    wa = (torch.randn(5, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    wb = (torch.randn(5, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()
+    wc = (torch.randn(6, C, C, device="cuda", generator=g) / C ** 0.5).bfloat16()        # slot 5 = out_proj.weight
+    ba, bb = (torch.randn(5, C, device="cuda", generator=g) * 0.3 for _ in range(2))
+    bc = torch.randn(6, C, device="cuda", generator=g) * 0.3
+    hbuf = torch.randn(M, 4 * C, device="cuda", generator=g).bfloat16()
+    att = hbuf[:, 3 * C:]
+    w_ab = torch.stack([wa.reshape(5, C // 64, 64, C), wb.reshape(5, C // 64, 64, C)], dim=2).reshape(5 * 2 * C, C).contiguous()
+    b_ab = torch.stack([ba.reshape(5, C // 64, 64), bb.reshape(5, C // 64, 64)], dim=2).reshape(5 * 2 * C).contiguous()
+    x0 = torch.randn(M, C, device="cuda", generator=g)
+    x = x0.clone()
+    w_c, b_c = wc.reshape(6 * C, C).contiguous(), bc.reshape(6 * C).contiguous()
+    h.mlp_fused_attn(xm, w_ab, b_ab, w_c, b_c, att, x, M, C, e1, e2)
+    ref = att.double() @ wc[5].double().t() + bc[5].double()
+    for e in (0, 1 + e1, 1 + e2):
+        hh = (xm.double() @ wa[e].double().t() + ba[e].double()) * torch.relu(xm.double() @ wb[e].double().t() + bb[e].double())
+        ref += hh.bfloat16().double() @ wc[e].double().t() + bc[e].double()
+    torch.cuda.synchronize()
+    assert h.device_fault() == 0
+    assert _rel(x - x0, ref) < 2e-3
