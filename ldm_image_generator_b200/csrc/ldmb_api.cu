@@ -784,7 +784,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   if (fused_ffn) {
     // C = 128 / 256: a|b GEMM, gate and c GEMM in one kernel, h stays on the SM; in attention blocks the out_proj rides along
     const bool att_in_mlp = w.attn && mlp_fused_att_supported(M, C);
-    CKLP(PK_FFN_AB, 2.0 * M * (double)C * 9 * C,
+    CKLP(PK_FFN_AB, 2.0 * M * (double)C * (att_in_mlp ? 10 : 9) * C,
          launch_mlp_fused(h->tc, u.xm.p, w.w_ab, w.b_ab, w.w_c, w.b_c, x, M, C, (w.attn ? 6 : 5) * C, pl, 0, 0, nullptr, 0, st,
                           conv_split > 0 ? tc_num_sms(h->tc) - u.split_free : 0, att_in_mlp ? toff(h, u.hbuf.p, 3LL * C) : nullptr, ldh));
     if (w.attn && !att_in_mlp && (rc = gemm(h, c, st, PK_FFN_C))) return rc;
