@@ -104,6 +104,7 @@ struct UNetState {
   // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
   // 3 = fork only in the fused feed-forward blocks (C <= 256), 4 = only in the two-GEMM blocks
   int fork_mode = getenv("LDMB_FORK_MODE") ? atoi(getenv("LDMB_FORK_MODE")) : 5;     // 5: SM-partitioned (run_block); 1: plain early fork; 2: late fork; 3 / 4: fork only the fused / two-GEMM blocks
+  int attn_part = getenv("LDMB_ATTN_PART") ? atoi(getenv("LDMB_ATTN_PART")) : 0;   // attention blocks at C >= 512, partitioned mode: 1 = conv beside a capped in-projection GEMM (a|b GEMM then uncapped)
   int attn_fused_fork = getenv("LDMB_ATTN_FUSED_FORK") ? atoi(getenv("LDMB_ATTN_FUSED_FORK")) : 2;   // attention blocks at C <= 256: 0 = conv serial, 1 = forked at the start of the block, 2 = forked after the attention core
   int fork_fused = getenv("LDMB_FORK_FUSED") ? atoi(getenv("LDMB_FORK_FUSED")) : 3;   // fork the conv beside the fused feed-forward: bit 0 at C = 128, bit 1 at C = 256
   // fork mode 5, fused feed-forward blocks (C <= 256): the conv is split over two launches -- the first conv_split / 1000 of its tiles
@@ -766,7 +767,16 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   };
   // attention blocks in partitioned mode: the in-projection GEMM and the attention core want the whole machine (a conv beside them
   // stretched the core from 13 to 30 us), so the conv is forked after them, beside the a|b GEMM that leaves it its SMs
-  const bool fork_after_attn = fork && !late && w.attn && (ab_cap > 0 || (fused_ffn && u.attn_fused_fork == 2));
+  // (LDMB_ATTN_PART=1: instead beside the in-projection GEMM, capped to the pairs its tile rounds need -- 96 / 48 tiles take 2 / 1 rounds
+  // on 48 pairs as on 74 -- and the a|b GEMM then gets the whole machine)
+  int qkv_cap = 0;
+  if (fork && !late && w.attn && ab_cap > 0 && u.attn_part == 1) {
+    const int sms = tc_num_sms(h->tc), pairs = sms / 2;
+    const long long tiles = (long long)((M + 255) / 256) * ((3 * C + 255) / 256);
+    const int rounds = (int)((tiles + pairs - 1) / pairs), need = (int)((tiles + rounds - 1) / rounds);
+    if (sms - 2 * need >= u.part_min_free) { qkv_cap = 2 * need; part_conv_cap = sms - 2 * need; ab_cap = 0; }
+  }
+  const bool fork_after_attn = fork && !late && w.attn && qkv_cap == 0 && (ab_cap > 0 || (fused_ffn && u.attn_fused_fork == 2));
   if (fork && !late && !fork_after_attn) {
     if ((rc = fork_conv_now(part_conv_cap))) return rc;
   } else if (!fork && !fused_nc && (rc = grouped_conv(h, u.xm.p, w.w_g, w.b_g, x, B, Hl, Wl, C, pl, st, false))) return rc;
@@ -774,6 +784,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     GemmDesc d = gd();
     d.A = u.xm.p; d.lda = C; d.W = w.w_in; d.ldw = C; d.bias = w.b_in; d.out = u.qkv.p; d.ldo = 3 * C;
     d.M = M; d.N = 3 * C; d.K = C; d.epi = EPI_STORE; d.plan = pl;
+    d.max_ctas = qkv_cap;
     if ((rc = gemm(h, d, st, PK_QKV))) return rc;
     const bool global = Hl <= kWindow && Wl <= kWindow;      // attention.py:15-16
     if ((rc = window_attention(h, u.qkv.p, u.xm.p, w.b_in, toff(h, u.hbuf.p, 3LL * C), ldh, B, Hl, Wl, C, global ? Hl : kWindow,
