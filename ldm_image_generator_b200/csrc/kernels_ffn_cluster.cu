@@ -57,7 +57,7 @@ struct FfnArgs {
   const float* b_ab; const float* b_c;
   const int* plan; int e1, e2;          // plan entry {skip, e1, e2, -} of the block, or explicit experts when NULL
   int M;
-  int dbg;                              // debug: 1 = gate epilogue writes nothing, 2 = no GEMM2 MMAs, 4 = no GEMM1 MMAs, 8 = no x update, 16 = no h copies to the peers
+  int dbg;                              // debug (LDMB_MLP_DBG): 1 = gate epilogue writes nothing, 2 = no GEMM2 MMAs, 4 = no GEMM1 MMAs, 8 = no x update, 16 = no h copies to the peers
   int nsteps;                           // debug: run only the first nsteps of the schedule (NSTEPS = all)
   int* progress;                        // debug: [grid][64] %globaltimer stamps (leader MMA warp: start of step s at [s]; epilogue warp 2: [32 + 4c + k])
   signed char sched[NSTEPS + 2];        // the MMA warp's static order: v >= 0: GEMM1 of this pair's chunk v; v < 0: GEMM2 of chunk -v-1
@@ -235,7 +235,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int kb = 0; ok && kb < NKB; ++kb) issue(&tmWab, kb * 64, row);
       } else {                         // GEMM2 of chunk u: Wc rows = this pair's output columns, k = the chunk's 64 hidden units
         const int u = -v - 1, e = u / NKB, jj = u % NKB;
-        if (!(a.dbg & 128)) issue(&tmWc, jj * 64, slot_of(e) * C + (int)pr * N2 + (int)rk * 64);
+        issue(&tmWc, jj * 64, slot_of(e) * C + (int)pr * N2 + (int)rk * 64);
       }
     }
     if (nsteps > 0 && !xm_loaded) load_xm();
@@ -293,7 +293,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           commit(&w_empty[stage], pair_mask);
           // consumed here: one of the four arrivals the pair that gates the slot's NEXT chunk (u + HS) waits for.  (Signalling only that
           // pair keeps every h_free phase observed by its waiter -- a parity wait that skips phases passes vacuously.)
-          if (!(a.dbg & 32) && u + HS < NU) commit(&h_free[ih], static_cast<uint16_t>(3u << (2 * ((u + HS) % NP))));
+          if (u + HS < NU) commit(&h_free[ih], static_cast<uint16_t>(3u << (2 * ((u + HS) % NP))));
           if (++stage == WS) { stage = 0; phase ^= 1; }
         }
       }
@@ -304,11 +304,11 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       // the leader's MMAs read this CTA's half of every h chunk: tell it when that half has landed
       for (int s = 0; ok && s < nsteps; ++s) {
         const int v = a.sched[s];
-        if (v >= 0 || (a.dbg & 256)) continue;
+        if (v >= 0) continue;
         STAMP(s);
         const int u = -v - 1, ih = u % HS;
-        if (!(a.dbg & 2048) && !wait_bar(&h_full[ih], (u / HS) & 1, s_abort, fault, 48)) { ok = false; break; }
-        if (issuer && !(a.dbg & 64)) arrive_remote(mapa(ptx::smem_u32(&h_peer[ih]), crank & ~1u));
+        if (!wait_bar(&h_full[ih], (u / HS) & 1, s_abort, fault, 48)) { ok = false; break; }
+        if (issuer) arrive_remote(mapa(ptx::smem_u32(&h_peer[ih]), crank & ~1u));
         __syncwarp();
       }
     }
@@ -366,17 +366,15 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (!wait_bar(&h_written[id], (c / ND1) & 1, s_abort, fault, 53)) { ok = false; break; }     // the whole chunk is written
       STAMP(32 + 4 * c + 2);
       if (threadIdx.x == 64) {
-        ptx::mbar_arrive(&h_full[ih]);
-        if (!(a.dbg & 16)) {                                          // local consumer (MMA / relay warp of this CTA)
+        ptx::mbar_arrive(&h_full[ih]);                                          // local consumer (MMA / relay warp of this CTA)
         const uint32_t src = ptx::smem_u32(hs + ih * H_BYTES), bar = ptx::smem_u32(&h_full[ih]);
 #pragma unroll
         for (uint32_t p2 = 0; p2 < NP; ++p2) {
-          if (p2 == pr) continue;
+          if (p2 == pr || (a.dbg & 16)) continue;
           const uint32_t dst_rank = 2 * p2 + rk;                               // same half of the row tile in the other pairs
           const uint32_t rbar = mapa(bar, dst_rank);
           arrive_expect_tx_remote(rbar, H_BYTES);                              // the chunk's one arrival on the peer's h_full + its byte count
           bulk_copy_to_cluster(mapa(src, dst_rank), src, H_BYTES, rbar);
-        }
         }
       }
       __syncwarp();
