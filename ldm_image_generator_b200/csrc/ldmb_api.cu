@@ -748,10 +748,13 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   if (fork && !fused_ffn && u.fork_mode == 5) {
     const int sms = tc_num_sms(h->tc), pairs = sms / 2;
     const long long tiles = (long long)((M + 255) / 256) * ((6 * C + 255) / 256);
-    int rounds = (int)((tiles + pairs - 1) / pairs);
-    int need = (int)((tiles + rounds - 1) / rounds);
-    if (sms - 2 * need < u.part_min_free) { ++rounds; need = (int)((tiles + rounds - 1) / rounds); }
-    if (need < pairs && sms - 2 * need >= C / 64) { ab_cap = 2 * need; part_conv_cap = sms - 2 * need; }
+    const int rounds0 = (int)((tiles + pairs - 1) / pairs);
+    // the fewest rounds (the GEMM's own count, or one more if that is at most a third longer) that leave the conv part_min_free SMs;
+    // large batches have many rounds and nothing to gain: no partition, the plain early fork
+    for (int rounds = rounds0; rounds <= rounds0 + 1 && 3 * rounds <= 4 * rounds0; ++rounds) {
+      const int need = (int)((tiles + rounds - 1) / rounds);
+      if (sms - 2 * need >= u.part_min_free && sms - 2 * need >= C / 64) { ab_cap = 2 * need; part_conv_cap = sms - 2 * need; break; }
+    }
   }
   const bool late = conv_cap > 0;
   // fused feed-forward blocks in partitioned mode: conv part 1 beside the capped feed-forward kernel, part 2 after the join
