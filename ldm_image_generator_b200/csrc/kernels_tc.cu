@@ -43,6 +43,9 @@ struct TcTiling {
   int splits, kb_per;   // split-K (EPI_ACCUM_F32 through TMA reduce-add only): tile t covers k-blocks [sp*kb_per, ...)
   int out_col_b, out_row_b;   // per-batch (grid z) column / row offset of the output tile in the out tensor map
   int ast_ppm, ast_tpp;       // A-stationary mode: CTA pairs per m-tile, consecutive n-tiles per pair
+  int ast_persist;            // A-stationary, persistent: pair p walks the m-tiles p, p + P, ... and takes ALL n-tiles of each (A loaded once per m-tile)
+  int ast_nbuf;               //   A buffers (an m-tile's k-block tiles each): the next m-tile's A loads while this one's n-tiles run
+  int ast_bres;               //   B resident: every (n-tile, k-block) tile of B sits in its own ring slot for the whole kernel
 };
 
 // CG = CTAs per tile: 1 (128 x BN per CTA) or 2 (a CTA pair computes 256 x BN with cta_group::2; each CTA stages its
@@ -131,8 +134,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + STAGES_MAX;
   uint64_t* tfull = empty + STAGES_MAX;
   uint64_t* tempty = tfull + 2;
-  uint64_t* a_full = tempty + 2;                                 // [kAstMaxKb] (AST)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + kAstMaxKb);
+  uint64_t* a_full = tempty + 2;                                 // [kAstMaxKb] (AST): (buffer, k-block)
+  uint64_t* a_empty = a_full + kAstMaxKb;                        // [2] (AST, persistent): the m-tile's last MMA has read the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);
 
@@ -142,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], kEpiWarps * CG); }
-    if (AST) for (int i = 0; i < kAstMaxKb; ++i) ptx::mbar_init(&a_full[i], 1);
+    if (AST) { for (int i = 0; i < kAstMaxKb; ++i) ptx::mbar_init(&a_full[i], 1); for (int i = 0; i < 2; ++i) ptx::mbar_init(&a_empty[i], 1); }
     *s_abort = 0;
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
@@ -177,11 +181,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // this CTA (pair)'s tiles: t_first + i * t_step, i < t_count.  Default: strided over the persistent grid.  AST: pair p owns ast_tpp
   // consecutive n-tiles of m-tile p / ast_ppm.
   int t_first = blockIdx.x / CG, t_step = gridDim.x / CG, t_count = total_tiles > t_first ? (total_tiles - t_first + t_step - 1) / t_step : 0;
-  if (AST) {
+  const bool ast_p = AST && tl.ast_persist != 0;
+  if (AST && !ast_p) {
     const int pair = blockIdx.x / CG, mt = pair / tl.ast_ppm, nt0 = (pair % tl.ast_ppm) * tl.ast_tpp;
     t_first = mt * tl.n_tiles + nt0; t_step = 1;
     t_count = (skip_block || mt >= tl.m_tiles || nt0 >= tl.n_tiles) ? 0 : min(tl.ast_tpp, tl.n_tiles - nt0);
   }
+  if (ast_p) {
+    const int my_mt = t_first < tl.m_tiles ? (tl.m_tiles - t_first + t_step - 1) / t_step : 0;     // t_first = pair, t_step = pairs
+    t_count = skip_block ? 0 : my_mt * tl.n_tiles;
+  }
+  // tile index of this pair's ti-th tile
+  auto tile_of = [&](int ti) -> int {
+    return ast_p ? (t_first + (ti / tl.n_tiles) * t_step) * tl.n_tiles + ti % tl.n_tiles : t_first + ti * t_step;
+  };
+  // AST: which A buffer / use count the ti-th tile reads, and whether it is the first / last n-tile of its m-tile
+  const int ast_nbuf = AST ? (tl.ast_nbuf > 0 ? tl.ast_nbuf : 1) : 1;
   const bool is_producer = warp == 0;          // the producer warp waits for the previous kernel only after its weight prefetch
   if (!is_producer) {
     pdl_wait();
@@ -202,8 +217,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // Weights are never written by a kernel of the step: the B tiles of the first pipeline fill are requested
       // while the previous kernel is still draining; only the activation (A) loads wait for it.
       int pre = 0;
+      if (AST && tl.ast_bres) {
+        // every (n-tile, k-block) tile of B into its own slot, once, while the previous kernel drains (weights)
+        if (t_count > 0) {
+          for (int nt = 0; nt < tl.n_tiles; ++nt)
+            for (int kb = 0; kb < tl.num_kb; ++kb) {
+              const int slot = nt * tl.num_kb + kb;
+              int brow, bcol;
+              b_coords(0, nt * BN, kb * BK, brow, bcol);
+              if (issuer) {
+                if (leader) ptx::mbar_arrive_expect_tx(&full[slot], Cfg::STAGE_BYTES * CG);
+                ptx::tma_load_2d_2sm(tiles + slot * Cfg::STAGE_BYTES, &tmB, &full[slot], bcol, brow);
+              }
+            }
+        }
+      } else
       {
-        const int t = t_first;
+        const int t = tile_of(0);
         if (t_count > 0) {
           const int sp = t / tiles_per_split, ts = t % tiles_per_split;
           const int z = ts / tiles_per_z, nt = (ts % tiles_per_z) % tl.n_tiles;
@@ -223,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       pdl_wait();
       if (issuer) trace_stamp(trace, 2);                         // previous kernel complete (producer's view)
-      if (AST && AMODE == AM_ROWS && t_count > 0 && issuer) {    // the pair's 256 x K block of A, once: one barrier per k-block so the MMAs start on the first
+      if (AST && !ast_p && AMODE == AM_ROWS && t_count > 0 && issuer) {    // the pair's 256 x K block of A, once: one barrier per k-block so the MMAs start on the first
         const int m0r = (t_first / tl.n_tiles) * (BM * CG) + (int)rank * BM;
         for (int kb = 0; kb < tl.num_kb; ++kb) {
           if (leader) ptx::mbar_arrive_expect_tx(&a_full[kb], Cfg::A_BYTES * CG);
@@ -233,12 +263,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();
       uint32_t stage = 0, phase = 0;
-      for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
+      for (int ti = 0; ti < t_count; ++ti) {
+        const int t = tile_of(ti);
         const int sp = t / tiles_per_split, ts = t % tiles_per_split;
         const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
         const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
         const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
         const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
+        if (ast_p && nt == 0) {
+          // a new m-tile: its A k-block tiles into the next buffer (the buffer's previous m-tile must have been consumed)
+          const int i = ti / tl.n_tiles, ab = i % ast_nbuf;
+          if (i >= ast_nbuf) wait_bar(&a_empty[ab], ((i / ast_nbuf) - 1) & 1, s_abort, fault, 6);
+          if (issuer) {
+            for (int kb = 0; kb < tl.num_kb; ++kb) {
+              if (leader) ptx::mbar_arrive_expect_tx(&a_full[ab * tl.num_kb + kb], Cfg::A_BYTES * CG);
+              ptx::tma_load_2d_2sm(a_res + (ab * tl.num_kb + kb) * Cfg::A_BYTES, &tmA, &a_full[ab * tl.num_kb + kb], kb * BK, m0);
+            }
+          }
+          __syncwarp();
+        }
+        if (AST && tl.ast_bres) continue;                        // B is resident: nothing to stream per tile
         int b0 = 0, h0 = 0, w0 = 0;
         if (AMODE == AM_CONV3) {
           const int hw = d.cH * d.cW;
@@ -288,19 +332,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool issuer = ptx::elect_one();
       constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
+      for (int ti = 0; ti < t_count; ++ti) {
+        const int t = tile_of(ti);
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const int kb0 = (t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
+        // AST: the A buffer of this tile's m-tile; its k-block barriers are waited for by the m-tile's first n-tile
+        const int a_i = ast_p ? ti / tl.n_tiles : 0, a_buf = a_i % ast_nbuf, a_nt = ast_p ? ti % tl.n_tiles : ti;
+        const uint32_t a_par = static_cast<uint32_t>((a_i / ast_nbuf) & 1);
+        const bool bres = AST && tl.ast_bres != 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (AST && ti == 0) wait_bar(&a_full[kb], 0, s_abort, fault, 5);
-          wait_bar(&full[stage], phase, s_abort, fault, 3);
+          if (AST && a_nt == 0) wait_bar(&a_full[a_buf * tl.num_kb + kb], a_par, s_abort, fault, 5);
+          const uint32_t slot = bres ? static_cast<uint32_t>(a_nt * tl.num_kb + kb) : stage;
+          if (!bres) wait_bar(&full[stage], phase, s_abort, fault, 3);
+          else if (a_i == 0) wait_bar(&full[slot], 0, s_abort, fault, 3);       // resident B: landed once, stays (a poll of a completed barrier still costs ~90 clk)
           if (issuer && ti == 0 && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           // one descriptor per operand tile, k offsets added in 16-byte units (the MMA thread is issue-bound, see kernels_gconv.cu)
-          const uint64_t s_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + stage * Cfg::STAGE_BYTES));
-          const uint64_t a_desc = AST ? ptx::smem_desc_sw128(ptx::smem_u32(a_res + kb * Cfg::A_BYTES)) : s_desc;
+          const uint64_t s_desc = ptx::smem_desc_sw128(ptx::smem_u32(tiles + slot * Cfg::STAGE_BYTES));
+          const uint64_t a_desc = AST ? ptx::smem_desc_sw128(ptx::smem_u32(a_res + (a_buf * tl.num_kb + kb) * Cfg::A_BYTES)) : s_desc;
           const uint64_t b_desc = AST ? s_desc : s_desc + Cfg::A_BYTES / 16;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -309,10 +360,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (issuer) { if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]); }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (!bres) {
+            if (issuer) { if (CG == 2) ptx::umma_commit_2sm(&empty[stage], 3); else ptx::umma_commit(&empty[stage]); }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
+        if (ast_p && a_nt == tl.n_tiles - 1) { if (issuer) ptx::umma_commit_2sm(&a_empty[a_buf], 3); __syncwarp(); }   // the m-tile's A buffer may be reloaded
         if (issuer) { if (CG == 2) ptx::umma_commit_2sm(&tfull[as], 3); else ptx::umma_commit(&tfull[as]); }   // accumulator complete -> epilogue(s)
         __syncwarp();
         as ^= 1;
@@ -332,7 +386,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
-    for (int ti = 0, t = t_first; ti < t_count; ++ti, t += t_step) {
+    for (int ti = 0; ti < t_count; ++ti) {
+      const int t = tile_of(ti);
       const int sp = t / tiles_per_split, ts = t % tiles_per_split;
       const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
       const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
@@ -788,6 +843,7 @@ static cudaError_t launch_tc_inst(TcContext* ctx, const CUtensorMap& tmA, const 
   }
   int grid = tl.total * CG < ctx->num_sms ? tl.total * CG : (ctx->num_sms / CG) * CG;
   if (AST) grid = tl.m_tiles * tl.ast_ppm * CG;            // one pair per (m-tile, run of ast_tpp n-tiles)
+  if (AST && tl.ast_persist) { const int pairs = ctx->num_sms / CG; grid = (tl.m_tiles < pairs ? tl.m_tiles : pairs) * CG; }   // persistent over the m-tiles
   if (!AST && tc_knobs().grid > 0 && tc_knobs().grid < grid) grid = (tc_knobs().grid / CG) * CG;   // debug
   if (!AST && d.max_ctas >= CG && d.max_ctas < grid) grid = (d.max_ctas / CG) * CG;
   cudaLaunchConfig_t cfg;
@@ -822,6 +878,7 @@ const TcKnobs& tc_knobs() {
     t.mlp_dbg = geti("LDMB_MLP_DBG", 0);
     t.gconv_dbg = geti("LDMB_GCONV_DBG", 0);
     t.attn_dbg = geti("LDMB_ATTN_DBG", 0);
+    t.astp = geti("LDMB_TC_ASTP", 0);        // 1: persistent A-stationary tiling for the in-projection GEMMs at C <= 256
     t.ast = geti("LDMB_TC_AST", 0);          // 1: A-stationary tiling for bf16-out K <= 512 GEMMs (measured slower: 17.7 vs 15.8 us at M4096 N3072 K512, see profiles/r2_experiment_a_stationary.txt)
     return t;
   }();
@@ -860,6 +917,7 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
   tl.dbg = tc_knobs().dbg;
   tl.TW = tl.TH = tl.TB = 0;
   tl.ast_ppm = tl.ast_tpp = 0;
+  tl.ast_persist = tl.ast_nbuf = tl.ast_bres = 0;
 
   CUtensorMap tmA, tmB;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
@@ -965,10 +1023,21 @@ static cudaError_t launch_gemm_tc_impl(TcContext* ctx, const GemmDesc& d, cudaSt
     int tpp = (tl.total + pairs - 1) / pairs;
     if (tpp > tl.n_tiles) tpp = tl.n_tiles;          // more m-tiles than pairs: one pair per m-tile (all its n-tiles), several waves of CTAs
     const int ppm = (tl.n_tiles + tpp - 1) / tpp;
-    if (tpp >= 2 && (tl.m_tiles * ppm <= pairs || tc_knobs().ast >= 2)) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
+    if (tpp >= 2 && (tl.m_tiles * ppm <= pairs || tc_knobs().ast == 2)) { ast = true; tl.ast_tpp = tpp; tl.ast_ppm = ppm; }
+  }
+  // Persistent A-stationary (LDMB_TC_ASTP, in-projection GEMMs at C <= 256: K = C, N = 3C, many more m-tiles than CTA pairs): pair p walks
+  // the m-tiles p, p + P, ..., loads each m-tile's A block ONCE (double buffered) and runs all its n-tiles against it; where all of B fits
+  // the ring's slots it is loaded once and stays.  The strided grid re-reads A once per n-tile (3x) and B once per tile.
+  if (tc_knobs().astp && !ast && d.amode == AM_ROWS && cg == 2 && (bn == 256 || bn == 128) && batch == 1 && tl.splits == 1 && tl.tma_out &&
+      d.epi == EPI_STORE && d.sel == 0 && tl.num_kb <= 4 && d.a_koff_b == 0 && tl.n_tiles >= 2 && tl.m_tiles > ctx->num_sms / 2) {
+    ast = true; tl.ast_persist = 1; tl.ast_ppm = 1; tl.ast_tpp = tl.n_tiles;
+    tl.ast_nbuf = kAstMaxKb / tl.num_kb >= 2 ? 2 : 1;
+    const int slots = bn == 256 ? TcCfg<256, 2, true>::STAGES : TcCfg<128, 2, true>::STAGES;
+    tl.ast_bres = tl.n_tiles * tl.num_kb <= slots ? 1 : 0;
   }
   if (ctas_only != nullptr) {
     int grid = ast ? tl.m_tiles * tl.ast_ppm * cg : (tl.total * cg < ctx->num_sms ? tl.total * cg : (ctx->num_sms / cg) * cg);
+    if (ast && tl.ast_persist) grid = (tl.m_tiles < ctx->num_sms / cg ? tl.m_tiles : ctx->num_sms / cg) * cg;
     if (!ast && d.max_ctas >= cg && d.max_ctas < grid) grid = (d.max_ctas / cg) * cg;
     *ctas_only = grid;
     return cudaSuccess;

@@ -8,7 +8,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // Debug / tuning knobs, read from the environment ONCE (first use), never on the launch path.
 struct TcKnobs {
-  int grid, stages, dbg, splits, force_cg, no_splitk, mlp_dbg, gconv_dbg, attn_dbg, ast;
+  int grid, stages, dbg, splits, force_cg, no_splitk, mlp_dbg, gconv_dbg, attn_dbg, ast, astp;
 };
 const TcKnobs& tc_knobs();
 

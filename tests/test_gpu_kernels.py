@@ -19,7 +19,8 @@ def _rel(a, b):
 
 GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (1000, 384, 512), (4096, 768, 128), (130, 64, 64), (512, 96, 192),
                (16, 1024, 1024), (8192, 256, 1536), (1024, 3072, 512),
-               (4096, 3072, 512), (16384, 768, 256), (4096, 1536, 512), (5000, 1280, 448)]     # A-stationary tilings (bf16-out, K <= 512, > 74 pair tiles)
+               (4096, 3072, 512), (16384, 768, 256), (4096, 1536, 512), (5000, 1280, 448),     # A-stationary tilings (bf16-out, K <= 512, > 74 pair tiles)
+               (65536, 384, 128), (32768, 768, 256), (20000, 640, 192)]                       # persistent A-stationary (more m-tiles than CTA pairs, K <= 256)
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)

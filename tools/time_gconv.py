@@ -12,5 +12,6 @@ for lvl in range(4):
     x = [torch.randn(B, H, H, C, device="cuda") for _ in range(3)]
     w = torch.randn(C, 576, device="cuda").bfloat16(); b = torch.zeros(C, device="cuda")
     us = timeit(lambda i: h.grouped_conv3x3(xm[i % 3], w, b, x[i % 3], B, H, H, C))
-    print(f"gconv level {lvl} (C={C}, {H}x{H}): {us:6.1f} us")
+    ug = timeit(lambda i: h.grouped_conv3x3(xm[i % 3], w, b, x[i % 3], B, H, H, C, force_generic=True))
+    print(f"gconv level {lvl} (C={C}, {H}x{H}): halo-patch kernel {us:6.1f} us | generic 9-tap-load implicit GEMM {ug:6.1f} us")
 assert h.device_fault() == 0
