@@ -918,8 +918,12 @@ __global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __r
                                                                  float* __restrict__ out, uint8_t* __restrict__ out_u8,
                                                                  int B, int H, int W, int C, int Cout) {
   pdl_wait();
-  constexpr int PPW = 32 / G;                              // pixels per warp per iteration
-  const int lane = threadIdx.x & 31, gl = lane % G, gp = lane / G;
+  constexpr int PPW = 32 / G;                              // pixels per warp per pass
+  constexpr int UNR = 4;                                   // pixel groups per pass: UNR*ITERS independent 16-byte loads in flight per lane
+  constexpr int SUBS = 32 / (PPW * UNR);                   // passes per 32-pixel chunk
+  static_assert(SUBS >= 1 && SUBS * PPW * UNR == 32, "a warp finishes 32 consecutive pixels per chunk");
+  __shared__ float s_dot[8][4][32];                        // [warp][output channel][pixel of the chunk]: dot products, re-read pixel-per-lane
+  const int lane = threadIdx.x & 31, gl = lane % G, gp = lane / G, wib = threadIdx.x >> 5;
   const int M = B * H * W;
   float wr[ITERS][4][8];                                   // [pass][j][8 channels]; C = ITERS * 8 * G
 #pragma unroll
@@ -929,43 +933,50 @@ __global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __r
 #pragma unroll
       for (int e = 0; e < 8; ++e) wr[it][j][e] = j < Cout ? w[(long long)j * C + it * 8 * G + gl * 8 + e] : 0.f;
   const int wpg = (gridDim.x * blockDim.x) >> 5;
-  constexpr int UNR = 4;                                   // pixel groups per iteration: UNR*ITERS independent 16-byte loads in flight per lane
-  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (PPW * UNR); mb < M; mb += wpg * PPW * UNR) {
-    uint4 u[UNR][ITERS];
+  for (int mb = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; mb < M; mb += wpg * 32) {
+    // ---- phase 1: G lanes per pixel reduce the C channels (16-byte loads), every pixel's Cout dot products go to shared memory
 #pragma unroll
-    for (int r = 0; r < UNR; ++r) {
-      const int m = mb + r * PPW + gp;
+    for (int sub = 0; sub < SUBS; ++sub) {
+      uint4 u[UNR][ITERS];
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it)
-        u[r][it] = m < M ? __ldg(reinterpret_cast<const uint4*>(x + (long long)m * C + it * 8 * G + gl * 8)) : make_uint4(0u, 0u, 0u, 0u);
-    }
+      for (int r = 0; r < UNR; ++r) {
+        const int m = mb + (sub * UNR + r) * PPW + gp;
 #pragma unroll
-    for (int r = 0; r < UNR; ++r) {
-      const int m = mb + r * PPW + gp;
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const uint32_t w4[4] = {u[r][it].x, u[r][it].y, u[r][it].z, u[r][it].w};
-        float xv[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
-          xv[2 * k] = __low2float(h2); xv[2 * k + 1] = __high2float(h2);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) a[j] = fmaf(xv[e], wr[it][j][e], a[j]);
+        for (int it = 0; it < ITERS; ++it)
+          u[r][it] = m < M ? __ldg(reinterpret_cast<const uint4*>(x + (long long)m * C + it * 8 * G + gl * 8)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1)
+      for (int r = 0; r < UNR; ++r) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-      // the butterfly leaves every lane of the group with all sums: lane gl finishes output channel j = gl
-      if (gl < Cout && m < M) {
-        const int j = gl;
-        const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
-        float v = (j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]))) + bias[j];
+        for (int it = 0; it < ITERS; ++it) {
+          const uint32_t w4[4] = {u[r][it].x, u[r][it].y, u[r][it].z, u[r][it].w};
+          float xv[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
+            xv[2 * k] = __low2float(h2); xv[2 * k + 1] = __high2float(h2);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[j] = fmaf(xv[e], wr[it][j][e], a[j]);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+        // the butterfly leaves every lane of the group with all sums: lane gl publishes output channel j = gl
+        if (gl < 4) s_dot[wib][gl][(sub * UNR + r) * PPW + gp] = gl == 0 ? a[0] : (gl == 1 ? a[1] : (gl == 2 ? a[2] : a[3]));
+      }
+    }
+    __syncwarp();
+    // ---- phase 2: lane = pixel: + bias, + bilinear-upsampled running sum (vae.py:131), coalesced NCHW fp32 rows and HWC uint8 bytes
+    const int m = mb + lane;
+    if (m < M) {
+      const int ww = m % W, hh = (m / W) % H, b = m / (W * H);
+      for (int j = 0; j < Cout; ++j) {
+        float v = s_dot[wib][j][lane] + bias[j];
         if (prev) {
           const int Hs = H / 2, Ws = W / 2;
           const int i0 = hh >> 1, j0 = ww >> 1;
@@ -984,6 +995,7 @@ __global__ void __launch_bounds__(256) pointwise_out_warp_kernel(const bf16* __r
         }
       }
     }
+    __syncwarp();                                            // s_dot is rewritten by the next chunk
   }
 }
 
@@ -1212,7 +1224,7 @@ cudaError_t launch_nhwc_pointwise_out(const void* x, bool is_bf16, const float* 
   const unsigned grid = (unsigned)((M + 31) / 32);
   if (is_bf16 && Cout <= 4 && (C == 64 || C == 128 || C == 256 || C == 512) && M < (1LL << 31)) {
     const int G = C >= 256 ? 32 : C / 8;                   // lanes per pixel, 8 channels per lane per pass
-    const int g2 = grid_for((M * G + 3) / 4, 256, 148 * 8);
+    const int g2 = grid_for((long long)((M + 31) / 32) * 32, 256, 148 * 8);      // a warp per 32-pixel chunk
     const bf16* xb = (const bf16*)x;
     if (C == 512) launch_k((pointwise_out_warp_kernel<32, 2>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
     else if (C == 256) launch_k((pointwise_out_warp_kernel<32, 1>), g2, 256, 0, st, xb, w, bias, prev, out, out_u8, B, H, W, C, Cout);
