@@ -141,6 +141,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-role cycle accounting (compiled in with -DLDMB_TC_TRACE only; tools/trace_gemm_roles.py reads it through ldmb_debug_tc_trace)
+#ifdef LDMB_TC_TRACE
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+  auto lap = [&](int slot) { if (trace != nullptr) { const long long now = clock64(); tacc[slot] += now - tlast; tlast = now; } };
+#else
+  auto lap = [](int) {};
+#endif
 
   if (threadIdx.x == 0) trace_stamp(trace, 0);                 // kernel entry
   if (threadIdx.x == 0) {
@@ -191,6 +199,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int my_mt = t_first < tl.m_tiles ? (tl.m_tiles - t_first + t_step - 1) / t_step : 0;     // t_first = pair, t_step = pairs
     t_count = skip_block ? 0 : my_mt * tl.n_tiles;
   }
+  // tile t -> (split, batch z, m-tile, n-tile).  The common launch (one K slice, no batch) needs one division, not five: the epilogue
+  // warps spent ~700 clk per tile on this decode (tools/trace_gemm_roles.py) -- a third of a K = 128 tile.
+  const bool plain_tiles = tl.splits == 1 && tiles_per_z == tl.total;
+  auto decode = [&](int t, int& sp, int& z, int& mt, int& nt) {
+    if (plain_tiles) { sp = 0; z = 0; mt = t / tl.n_tiles; nt = t - mt * tl.n_tiles; return; }
+    sp = t / tiles_per_split;
+    const int ts = t - sp * tiles_per_split;
+    z = ts / tiles_per_z;
+    const int rem = ts - z * tiles_per_z;
+    mt = rem / tl.n_tiles; nt = rem - mt * tl.n_tiles;
+  };
   // tile index of this pair's ti-th tile
   auto tile_of = [&](int ti) -> int {
     return ast_p ? (t_first + (ti / tl.n_tiles) * t_step) * tl.n_tiles + ti % tl.n_tiles : t_first + ti * t_step;
@@ -235,8 +254,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const int t = tile_of(0);
         if (t_count > 0) {
-          const int sp = t / tiles_per_split, ts = t % tiles_per_split;
-          const int z = ts / tiles_per_z, nt = (ts % tiles_per_z) % tl.n_tiles;
+          int sp, z, mt_, nt;
+          decode(t, sp, z, mt_, nt);
           const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
           for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
             uint8_t* b_dst = tiles + pre * Cfg::STAGE_BYTES + (AST ? 0 : Cfg::A_BYTES);
@@ -265,9 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t stage = 0, phase = 0;
       for (int ti = 0; ti < t_count; ++ti) {
         const int t = tile_of(ti);
-        const int sp = t / tiles_per_split, ts = t % tiles_per_split;
-        const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
-        const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
+        int sp, z, mt, nt;
+        decode(t, sp, z, mt, nt);
         const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
         const int kb0 = sp * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
         if (ast_p && nt == 0) {
@@ -334,10 +352,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int ti = 0; ti < t_count; ++ti) {
         const int t = tile_of(ti);
+        lap(10);
         wait_bar(&tempty[as], aphase ^ 1, s_abort, fault, 2);
+        lap(8);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        const int kb0 = (t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
+        const int kb0 = (plain_tiles ? 0 : t / tiles_per_split) * tl.kb_per, kb1 = min(tl.num_kb, kb0 + tl.kb_per);
         // AST: the A buffer of this tile's m-tile; its k-block barriers are waited for by the m-tile's first n-tile
         const int a_i = ast_p ? ti / tl.n_tiles : 0, a_buf = a_i % ast_nbuf, a_nt = ast_p ? ti % tl.n_tiles : ti;
         const uint32_t a_par = static_cast<uint32_t>((a_i / ast_nbuf) & 1);
@@ -345,8 +365,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           if (AST && a_nt == 0) wait_bar(&a_full[a_buf * tl.num_kb + kb], a_par, s_abort, fault, 5);
           const uint32_t slot = bres ? static_cast<uint32_t>(a_nt * tl.num_kb + kb) : stage;
+          lap(10);
           if (!bres) wait_bar(&full[stage], phase, s_abort, fault, 3);
           else if (a_i == 0) wait_bar(&full[slot], 0, s_abort, fault, 3);       // resident B: landed once, stays (a poll of a completed barrier still costs ~90 clk)
+          lap(9);
           if (issuer && ti == 0 && kb == kb0) trace_stamp(trace, 4);   // first operands landed
           ptx::tc_fence_after();
           // one descriptor per operand tile, k offsets added in 16-byte units (the MMA thread is issue-bound, see kernels_gconv.cu)
@@ -373,6 +395,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (as == 0) aphase ^= 1;
       }
       if (issuer) trace_stamp(trace, 5);                               // all MMAs issued
+#ifdef LDMB_TC_TRACE
+      lap(10);
+      if (trace != nullptr && lane == 0 && blockIdx.x < 256) for (int i = 8; i < 11; ++i) trace[blockIdx.x * 16 + 16 * 256 + i] = tacc[i];
+#endif
     }
     __syncwarp();
   } else {
@@ -388,11 +414,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int slab_sel = 0;
     for (int ti = 0; ti < t_count; ++ti) {
       const int t = tile_of(ti);
-      const int sp = t / tiles_per_split, ts = t % tiles_per_split;
-      const int z = ts / tiles_per_z, rem = ts % tiles_per_z;
-      const int mt = rem / tl.n_tiles, nt = rem % tl.n_tiles;
+      int sp, z, mt, nt;
+      decode(t, sp, z, mt, nt);
       const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
       float* sb = s_bias + as * BN;
+      lap(0);
       if (!(tl.dbg & 8) || ti == 0)
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
@@ -406,7 +432,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sb[c] = bv;
       }
       if (!(tl.dbg & 8) || ti == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      lap(1);
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
+      lap(2);
       if (threadIdx.x == 64) trace_stamp(trace, ti == 0 ? 6 : 7);   // first / latest accumulator ready
       ptx::tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -424,9 +452,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int a0 = chalf * accw; a0 < BN; a0 += 2 * accw) {      // slabs interleaved between the two column warps
             if (n0 + a0 >= d.N) break;
             uint8_t* slab = staging + (ew * Cfg::SLABS + slab_sel % Cfg::SLABS) * Cfg::SLAB_BYTES;
+            lap(0);
             if (lane == 0) { if (Cfg::SLABS == 1) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>(); }   // the store that last used this slab has read it
             __syncwarp();
+            lap(3);
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
+            if (d.epi == EPI_STORE && d.act == ACT_NONE && !(tl.dbg & (16 | 32))) {
+              // in-projections: bias add only, both 32-column halves of the slab behind ONE TMEM round trip (the epilogue is issue- and
+              // latency-bound: tools/trace_gemm_roles.py)
+              uint32_t r0[32], r1[32];
+              ptx::tmem_ld_32x32(t_row + a0, r0);
+              ptx::tmem_ld_32x32(t_row + a0 + 32, r1);
+              ptx::tmem_ld_wait();
+              const uint32_t sba = ptx::smem_u32(sb + a0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 b0 = ptx::ld_shared_v4(sba + u * 32), b1 = ptx::ld_shared_v4(sba + u * 32 + 16);
+                ptx::st_shared_v4(srow + ((u ^ sw) << 4),
+                                  pack_bf16(__uint_as_float(r0[8 * u]) + b0.x, __uint_as_float(r0[8 * u + 1]) + b0.y),
+                                  pack_bf16(__uint_as_float(r0[8 * u + 2]) + b0.z, __uint_as_float(r0[8 * u + 3]) + b0.w),
+                                  pack_bf16(__uint_as_float(r0[8 * u + 4]) + b1.x, __uint_as_float(r0[8 * u + 5]) + b1.y),
+                                  pack_bf16(__uint_as_float(r0[8 * u + 6]) + b1.z, __uint_as_float(r0[8 * u + 7]) + b1.w));
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 b0 = ptx::ld_shared_v4(sba + 128 + u * 32), b1 = ptx::ld_shared_v4(sba + 128 + u * 32 + 16);
+                ptx::st_shared_v4(srow + (((4 + u) ^ sw) << 4),
+                                  pack_bf16(__uint_as_float(r1[8 * u]) + b0.x, __uint_as_float(r1[8 * u + 1]) + b0.y),
+                                  pack_bf16(__uint_as_float(r1[8 * u + 2]) + b0.z, __uint_as_float(r1[8 * u + 3]) + b0.w),
+                                  pack_bf16(__uint_as_float(r1[8 * u + 4]) + b1.x, __uint_as_float(r1[8 * u + 5]) + b1.y),
+                                  pack_bf16(__uint_as_float(r1[8 * u + 6]) + b1.z, __uint_as_float(r1[8 * u + 7]) + b1.w));
+              }
+            } else
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t r[32];
@@ -466,6 +523,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tmem_ld_wait();
                 }
                 const uint32_t sba = ptx::smem_u32(sb + a0 + half * 32);
+                if (d.act == ACT_NONE) {      // in-projections: bias add only (the epilogue is issue-bound: ~6 instructions per element with the activation)
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 ba = ptx::ld_shared_v4(sba + i * 16);
+                    v[4 * i] = __uint_as_float(r[4 * i]) + ba.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + ba.y;
+                    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + ba.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + ba.w;
+                  }
+                } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 ba = ptx::ld_shared_v4(sba + i * 16);
@@ -473,6 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const float t2 = __uint_as_float(r[4 * i + 2]) + ba.z, t3 = __uint_as_float(r[4 * i + 3]) + ba.w;
                   v[4 * i] = fmaxf(t0, 0.f) + ns * fminf(t0, 0.f); v[4 * i + 1] = fmaxf(t1, 0.f) + ns * fminf(t1, 0.f);
                   v[4 * i + 2] = fmaxf(t2, 0.f) + ns * fminf(t2, 0.f); v[4 * i + 3] = fmaxf(t3, 0.f) + ns * fminf(t3, 0.f);
+                }
                 }
               }
               if (!(tl.dbg & 32))
@@ -482,6 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                   pack_bf16(v[8 * u + 2], v[8 * u + 3]), pack_bf16(v[8 * u + 4], v[8 * u + 5]),
                                   pack_bf16(v[8 * u + 6], v[8 * u + 7]));
             }
+            lap(5);
             if (!(tl.dbg & 64)) ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -489,6 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (!(tl.dbg & 4)) ptx::tma_store_2d(&tmO, slab, ocol, orow);
               ptx::bulk_commit();
             }
+            lap(6);
             slab_sel ^= 1;
           }
         } else {   // EPI_STORE_F32 / EPI_ACCUM_F32: 32 fp32 columns per slab
@@ -669,15 +737,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      lap(0);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG == 2) ptx::mbar_arrive_leader(&tempty[as]); else ptx::mbar_arrive(&tempty[as]); }
+      lap(7);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
     if (tl.tma_out && lane == 0) ptx::bulk_wait_read<0>();  // the stores have read their smem slabs; the writes themselves complete with the grid
     __syncwarp();
     if (threadIdx.x == 64) trace_stamp(trace, 8);            // epilogue done
+#ifdef LDMB_TC_TRACE
+    if (trace != nullptr && threadIdx.x == 64 && blockIdx.x < 256) for (int i = 0; i < 8; ++i) trace[blockIdx.x * 16 + 16 * 256 + i] = tacc[i];
+#endif
   }
   ptx::tc_fence_before();
   __syncthreads();
