@@ -116,6 +116,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// packed fp32 pairs (sm_100 f32x2 pipe): two adds / multiplies per instruction in the issue-bound gate epilogue
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
 
 template <int BN, int AMODE, int CG, bool AST>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -504,11 +515,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sba = ptx::smem_u32(sb + a0 + half * 32);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+                  // (a + bias_a) * relu(b + bias_b): adds and the multiply as packed f32x2 (same roundings as the scalar form)
                   const float4 ba = ptx::ld_shared_v4(sba + i * 16), bg = ptx::ld_shared_v4(sba + 256 + i * 16);
-                  v[4 * i] = (__uint_as_float(r[4 * i]) + ba.x) * fmaxf(__uint_as_float(rb[4 * i]) + bg.x, 0.f);
-                  v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + ba.y) * fmaxf(__uint_as_float(rb[4 * i + 1]) + bg.y, 0.f);
-                  v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + ba.z) * fmaxf(__uint_as_float(rb[4 * i + 2]) + bg.z, 0.f);
-                  v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + ba.w) * fmaxf(__uint_as_float(rb[4 * i + 3]) + bg.w, 0.f);
+                  float2 a01 = add2(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(ba.x, ba.y));
+                  float2 a23 = add2(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(ba.z, ba.w));
+                  float2 g01 = add2(make_float2(__uint_as_float(rb[4 * i]), __uint_as_float(rb[4 * i + 1])), make_float2(bg.x, bg.y));
+                  float2 g23 = add2(make_float2(__uint_as_float(rb[4 * i + 2]), __uint_as_float(rb[4 * i + 3])), make_float2(bg.z, bg.w));
+                  g01.x = fmaxf(g01.x, 0.f); g01.y = fmaxf(g01.y, 0.f); g23.x = fmaxf(g23.x, 0.f); g23.y = fmaxf(g23.y, 0.f);
+                  a01 = mul2(a01, g01); a23 = mul2(a23, g23);
+                  v[4 * i] = a01.x; v[4 * i + 1] = a01.y; v[4 * i + 2] = a23.x; v[4 * i + 3] = a23.y;
                 }
                 if (!keep) {
 #pragma unroll
