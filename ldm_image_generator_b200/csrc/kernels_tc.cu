@@ -579,8 +579,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int a0 = chalf * 32; a0 < BN; a0 += 64) {
             if (n0 + a0 >= d.N) break;
             uint8_t* slab = staging + (ew * Cfg::SLABS + slab_sel % Cfg::SLABS) * Cfg::SLAB_BYTES;
+            lap(0);
             if (lane == 0) { if (Cfg::SLABS == 1) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>(); }
             __syncwarp();
+            lap(3);
             const uint32_t srow = ptx::smem_u32(slab) + lane * 128;
             uint32_t r[32];
             ptx::tmem_ld_32x32(t_row + a0, r);
@@ -603,6 +605,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < 8; ++u)
               ptx::st_shared_v4(srow + ((u ^ sw) << 4), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
                                 __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+            lap(5);
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {

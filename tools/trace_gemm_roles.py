@@ -7,15 +7,17 @@ import numpy as np, torch
 from ldm_image_generator_b200 import runtime
 h = runtime.Handle(torch.device("cuda", 0), "bf16")
 shapes = [(65536, 384, 128), (16384, 768, 256), (4096, 3072, 512)]
+mode = 0
 if len(sys.argv) > 3:
     shapes = [tuple(int(v) for v in sys.argv[1:4])]
+    mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # 0 bf16 store, 2 fp32 accumulate (residual GEMMs: split-K, TMA reduce-add)
 for (M, N, K) in shapes:
     A = torch.randn(M, K, device="cuda").bfloat16(); W = torch.randn(N, K, device="cuda").bfloat16()
-    bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3): h.gemm(A, W, bias, out, M, N, K)
+    bias = torch.randn(N, device="cuda"); out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if mode else torch.bfloat16)
+    for _ in range(3): h.gemm(A, W, bias, out, M, N, K, out_f32=mode)
     torch.cuda.synchronize()
     h.lib.ldmb_debug_tc_trace(h.h, 1, None, 0)
-    for _ in range(4): h.gemm(A, W, bias, out, M, N, K)
+    for _ in range(4): h.gemm(A, W, bias, out, M, N, K, out_f32=mode)
     buf = (C.c_int64 * (16 * 512))()
     h.lib.ldmb_debug_tc_trace(h.h, 1, buf, 512)
     h.lib.ldmb_debug_tc_trace(h.h, 0, None, 0)
