@@ -66,7 +66,8 @@ template <int BN, int CG> struct TcCfg<BN, CG, true> {
   static constexpr int SLAB_BYTES = 32 * 128;
   static constexpr int SLABS = 1;                            // one staging slab per epilogue warp (bf16 epilogues: one slab per tile and warp)
   static constexpr int STAGING_BYTES = kEpiWarps * SLABS * SLAB_BYTES;
-  static constexpr int FIXED_BYTES = 1024 + A_RES_BYTES + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
+  static constexpr int BIAS_FLOATS = BN == 256 ? 3072 : (BN == 128 ? 448 : 2 * BN);   // >= 2 * BN; sized so that no pipeline stage is lost
+  static constexpr int FIXED_BYTES = 1024 + A_RES_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_FLOATS * 4;
   static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int SMEM_BYTES = FIXED_BYTES + STAGES * STAGE_BYTES;
@@ -84,7 +85,9 @@ template <int BN, int CG> struct TcCfg<BN, CG, false> {
   static constexpr int SLABS = 2;
   static constexpr int A_RES_BYTES = 0;
   static constexpr int STAGING_BYTES = kEpiWarps * SLABS * SLAB_BYTES;   // per epilogue warp, double buffered
-  static constexpr int FIXED_BYTES = 1024 + STAGING_BYTES + BAR_BYTES + 2 * BN * 4;
+  // bias staging: the whole launch's bias vector when it fits (N <= BIAS_FLOATS, one K slice, no batch), else two tiles' worth
+  static constexpr int BIAS_FLOATS = BN == 256 ? 3072 : (BN == 128 ? 448 : 2 * BN);   // >= 2 * BN; sized so that no pipeline stage is lost
+  static constexpr int FIXED_BYTES = 1024 + STAGING_BYTES + BAR_BYTES + BIAS_FLOATS * 4;
   static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;       // 227 KB of dynamic smem per CTA
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int SMEM_BYTES = FIXED_BYTES + STAGES * STAGE_BYTES;
@@ -423,26 +426,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float ns = d.act == ACT_RELU ? 0.f : (d.act == ACT_LEAKY ? d.slope : 1.f);
     uint32_t as = 0, aphase = 0;
     int slab_sel = 0;
+    auto bias_of = [&](int z, int n) -> float {
+      const float* bp = d.bias + z * d.bias_off_b;
+      if (sel_k) { float bv = 0.f; for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; return bv; }
+      if (d.sel == 1) return bp[srow(n / d.sel_span) + n % d.sel_span];
+      return bp[n];
+    };
+    // The whole bias vector once per kernel where it fits: per tile the staging cost a global load and a 256-thread barrier on the
+    // epilogue's critical path (0.2 us per tile, tools/trace_gemm_roles.py).
+    const bool bias_all = plain_tiles && d.N <= Cfg::BIAS_FLOATS && t_count > 0 && !(tl.dbg & 8);
+    if (bias_all) {
+      for (int n = et; n < d.N; n += 32 * kEpiWarps) s_bias[n] = d.bias != nullptr ? bias_of(0, n) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    }
     for (int ti = 0; ti < t_count; ++ti) {
       const int t = tile_of(ti);
       int sp, z, mt, nt;
       decode(t, sp, z, mt, nt);
       const int m0 = mt * (BM * CG) + (int)rank * BM, n0 = nt * BN;
-      float* sb = s_bias + as * BN;
+      float* sb = bias_all ? s_bias + n0 : s_bias + as * BN;
       lap(0);
+      if (!bias_all)
       if (!(tl.dbg & 8) || ti == 0)
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
         const int n = n0 + c;
         float bv = 0.f;
-        if (n < d.N && d.bias != nullptr && sp == 0) {      // split-K: the bias rides with the first K slice
-          const float* bp = d.bias + z * d.bias_off_b;
-          if (sel_k) { for (int qq = 0; qq < d.K / d.sel_span; ++qq) bv += bp[srow(qq) + n]; }
-          else if (d.sel == 1) bv = bp[srow(n / d.sel_span) + n % d.sel_span];
-          else bv = bp[n];
-        }
+        if (n < d.N && d.bias != nullptr && sp == 0) bv = bias_of(z, n);      // split-K: the bias rides with the first K slice
         sb[c] = bv;
       }
-      if (!(tl.dbg & 8) || ti == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (!bias_all && (!(tl.dbg & 8) || ti == 0)) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       lap(1);
       wait_bar(&tfull[as], aphase, s_abort, fault, 4);
       lap(2);
