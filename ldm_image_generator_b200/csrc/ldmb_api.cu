@@ -99,6 +99,7 @@ struct UNetState {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_conv = getenv("LDMB_NO_FORK") == nullptr;
+  bool deterministic = false;          // ldmb_set_deterministic: no split-K, no two concurrent updaters of x
   // where the forked conv runs in the two-GEMM blocks (C >= 512): 1 (default) = from the norm on, beside the a|b GEMM; 2 = beside
   // the c-projection only, capped to the SMs that GEMM's grid leaves idle -- measured 22 % SLOWER end to end (16 CTAs walk 32 tiles
   // each, the block waits for them), kept as an experiment knob (profiles/r2_experiment_conv_fork_placement.txt);
@@ -725,7 +726,10 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   }
   // concurrent updaters of x must ALL be L2 reductions (halo conv reds, fused feed-forward / GEMM TMA reduce-adds): a shape
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
-  const bool fork = !fused_nc && u.fork_conv && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
+  // Deterministic mode keeps ONE concurrency: in the two-GEMM blocks the conv may run beside the a|b GEMM (which does not touch x) as long
+  // as it is joined BEFORE the c-projection -- every element of x still receives its two updates in a fixed order (conv, then c).
+  const bool det_fork = u.deterministic && !fused_ffn && u.fork_mode == 5 && getenv("LDMB_NO_FORK") == nullptr;
+  bool fork = !fused_nc && (u.fork_conv || det_fork) && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
                     ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !((u.fork_fused >> (C == 128 ? 0 : 1)) & 1)) &&
                     !(fused_ffn && w.attn && u.attn_fused_fork == 0);
   if (fork && !u.side_stream) {
@@ -756,6 +760,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
       if (sms - 2 * need >= u.part_min_free && sms - 2 * need >= C / 64) { ab_cap = 2 * need; part_conv_cap = sms - 2 * need; break; }
     }
   }
+  if (u.deterministic && fork && ab_cap == 0) fork = false;      // no SMs to give the conv: serial
   const bool late = conv_cap > 0;
   // fused feed-forward blocks in partitioned mode: conv part 1 beside the capped feed-forward kernel, part 2 after the join
   const int conv_split = (fork && fused_ffn && !w.attn && u.fork_mode == 5 && u.split_free >= C / 64) ? (C == 128 ? u.conv_split128 : u.conv_split256) : 0;
@@ -814,9 +819,10 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
     d.max_ctas = ab_cap;
     if ((rc = gemm(h, d, st, PK_FFN_AB))) return rc;
     if (late && (rc = fork_conv_now(conv_cap))) return rc;
+    if (fork && u.deterministic) CK(cudaStreamWaitEvent(st, u.ev_join, 0));     // the conv's update of x is complete before the c-projection's
     if ((rc = gemm(h, c, st, PK_FFN_C))) return rc;
   }
-  if (fork) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
+  if (fork && !u.deterministic) CK(cudaStreamWaitEvent(st, u.ev_join, 0));
   return LDMB_OK;
 }
 
@@ -1003,6 +1009,7 @@ extern "C" int ldmb_set_deterministic(ldmb_handle* h, int on) {
   if (!h) return LDMB_ERR_INVALID;
   tc_set_splitk(h->tc, on == 0);
   h->unet.fork_conv = on == 0 && getenv("LDMB_NO_FORK") == nullptr;
+  h->unet.deterministic = on != 0;
   h->unet.ws_epoch++;          // captured graphs hold the old launch set
   return LDMB_OK;
 }
