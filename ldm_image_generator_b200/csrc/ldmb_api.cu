@@ -98,7 +98,8 @@ struct UNetState {
   // captured graph) next to the block's GEMM chain, so its CTAs fill the SMs the GEMMs' partial last waves leave idle.
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool fork_conv = getenv("LDMB_NO_FORK") == nullptr;
+  const bool no_fork_env = getenv("LDMB_NO_FORK") != nullptr;      // read once (handle creation), like every knob
+  bool fork_conv = !no_fork_env;
   bool deterministic = false;          // ldmb_set_deterministic: no split-K, no two concurrent updaters of x
   // where the forked conv runs in the two-GEMM blocks (C >= 512): 1 (default) = from the norm on, beside the a|b GEMM; 2 = beside
   // the c-projection only, capped to the SMs that GEMM's grid leaves idle -- measured 22 % SLOWER end to end (16 CTAs walk 32 tiles
@@ -728,7 +729,7 @@ int run_block(ldmb_handle* h, const BlockW& w, int block_index, int B, int Hl, i
   // that would send the GEMM down a read-modify-write epilogue (CUDA-core fallback, unaligned x) is not forked
   // Deterministic mode keeps ONE concurrency: in the two-GEMM blocks the conv may run beside the a|b GEMM (which does not touch x) as long
   // as it is joined BEFORE the c-projection -- every element of x still receives its two updates in a fixed order (conv, then c).
-  const bool det_fork = u.deterministic && !fused_ffn && u.fork_mode == 5 && getenv("LDMB_NO_FORK") == nullptr;
+  const bool det_fork = u.deterministic && !fused_ffn && u.fork_mode == 5 && !u.no_fork_env;
   bool fork = !fused_nc && (u.fork_conv || det_fork) && h->bf16() && !h->force_simt && !h->prof_on && C % 128 == 0 && gconv_halo_supported(B, Hl, Wl, C) &&
                     ((fused_ffn && !w.attn) || tc_accum_is_reduction(c)) && !(u.fork_mode == 3 && !fused_ffn) && !(u.fork_mode == 4 && fused_ffn) && !(fused_ffn && !((u.fork_fused >> (C == 128 ? 0 : 1)) & 1)) &&
                     !(fused_ffn && w.attn && u.attn_fused_fork == 0);
@@ -1008,7 +1009,7 @@ extern "C" int ldmb_host_draw_plans(const uint32_t* raw, int64_t n_raw, int n_pl
 extern "C" int ldmb_set_deterministic(ldmb_handle* h, int on) {
   if (!h) return LDMB_ERR_INVALID;
   tc_set_splitk(h->tc, on == 0);
-  h->unet.fork_conv = on == 0 && getenv("LDMB_NO_FORK") == nullptr;
+  h->unet.fork_conv = on == 0 && !h->unet.no_fork_env;
   h->unet.deterministic = on != 0;
   h->unet.ws_epoch++;          // captured graphs hold the old launch set
   return LDMB_OK;
