@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Throughput of DDPM.sample_independent (per-image plans: the reference scripts' batch-1 loops computed as one batch) against the
+shared-plan batch and the batch-1 loop through this library (profiles/r1_per_image_plans_throughput.txt)."""
 import os, sys, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, random
 from ldm_image_generator_b200 import DDPM, UNet
